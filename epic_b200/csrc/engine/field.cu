@@ -1,0 +1,863 @@
+// field.cu -- see field.h.  Compiled with -fmad=false (bit-exact float arithmetic; every fused
+// multiply-add in the kernels is an explicit intrinsic).
+#include "field.h"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <unordered_map>
+#include <vector>
+
+#include "../kernels/aux_kernels.cuh"
+#include "../kernels/sweep2d.cuh"
+#include "../kernels/sweep3d.cuh"
+
+namespace epic_b200 {
+
+namespace {
+
+// libepic error codes (reference libepic/include/epic/error_codes.h:31-46)
+enum {
+    kSuccess = 0,
+    kConverged = 1,
+    kInvalidData = 2,
+    kInvalidCudaParam = 3,
+    kDeviceMalloc = 4,
+    kMemcpyToDevice = 5,
+    kMemcpyToHost = 6,
+    kDeviceFree = 7,
+    kKernelExecution = 8,
+    kDeviceSynchronize = 9
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// The driver entry point is looked up at run time so that the library has no link-time dependency
+// on libcuda.so (it must load, for symbol checks, on machines without a driver).
+EncodeTiledFn encode_tiled()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess) {
+            fn = (EncodeTiledFn)p;
+        }
+    }
+    return fn;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev)
+    {
+        cudaGetDevice(&prev);
+        if (prev != dev) {
+            cudaSetDevice(dev);
+        } else {
+            prev = -1;
+        }
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) {
+            cudaSetDevice(prev);
+        }
+    }
+};
+
+uint64_t round_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+
+template <class K>
+bool allow_smem(K kernel, size_t bytes)
+{
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) == cudaSuccess;
+}
+
+}  // namespace
+
+FieldConfig config_from_env()
+{
+    FieldConfig cfg;
+    if (const char *s = getenv("EPIC_MATH")) {
+        if (strcmp(s, "fast") == 0) {
+            cfg.math = MATH_FAST;
+        } else if (strcmp(s, "strict") != 0) {
+            fprintf(stderr, "Warning[epic_b200]: EPIC_MATH='%s' is neither 'strict' nor 'fast'; using strict.\n", s);
+        }
+    }
+    if (const char *s = getenv("EPIC_SWEEPS_PER_PASS")) {
+        cfg.sweeps_per_pass = atoi(s);
+    }
+    if (const char *s = getenv("EPIC_TILE_ROWS")) {
+        cfg.tile_rows = atoi(s);
+    }
+    if (const char *s = getenv("EPIC_DEVICE")) {
+        cfg.device = atoi(s);
+    }
+    return cfg;
+}
+
+int Field::create(Field **out, unsigned n, const uint64_t *gm, uint64_t row0, uint64_t rows, unsigned ghost,
+                  const FieldConfig &cfg)
+{
+    *out = nullptr;
+    if ((n != 2 && n != 3) || gm == nullptr || rows == 0) {
+        return kInvalidData;
+    }
+    for (unsigned i = 0; i < n; ++i) {
+        if (gm[i] == 0 || gm[i] > 0x7fffffffull) {
+            return kInvalidData;
+        }
+    }
+    if (row0 + rows > gm[0]) {
+        return kInvalidData;
+    }
+    Field *f = new Field();
+    f->cfg_ = cfg;
+    if (f->cfg_.device < 0) {
+        if (cudaGetDevice(&f->cfg_.device) != cudaSuccess) {
+            delete f;
+            return kDeviceMalloc;
+        }
+    }
+    DeviceGuard guard(f->cfg_.device);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, f->cfg_.device) != cudaSuccess) {
+        delete f;
+        return kDeviceMalloc;
+    }
+    if (prop.major < 10) {
+        fprintf(stderr, "Error[epic_b200]: this library contains sm_100a code only; device %d is sm_%d%d.\n",
+                f->cfg_.device, prop.major, prop.minor);
+        delete f;
+        return kInvalidCudaParam;
+    }
+    f->sms_ = prop.multiProcessorCount;
+    f->n_ = n;
+    for (unsigned i = 0; i < n; ++i) {
+        f->gm_[i] = gm[i];
+    }
+    f->row0_ = row0;
+    f->rows_ = rows;
+    f->ghost_ = ghost;
+    f->grow0_ = (int64_t)row0 - (int64_t)ghost;
+    f->buf_layers_ = rows + 2ull * ghost;
+    f->own_lo_ = ghost;
+    f->own_hi_ = ghost + rows;
+    const uint64_t inner = gm[n - 1];
+    f->pitch_ = std::max<uint64_t>(round_up(inner, 32), (n == 2) ? (uint64_t)kTileW : 32ull);
+    f->mask_wpr_ = f->pitch_ / 32;
+    f->layer_floats_ = (n == 2) ? f->pitch_ : gm[1] * f->pitch_;
+
+    // Tile geometry (2-D): the largest tile that still gives every SM a CTA.
+    f->T_ = (n == 2) ? 4 : 1;
+    if (cfg.sweeps_per_pass > 0 && n == 2) {
+        f->T_ = std::min(cfg.sweeps_per_pass, 8);
+    }
+    if (n == 2) {
+        const int HC = 4 * ((f->T_ + 3) / 4);
+        const int out_w = kTileW - 2 * HC;
+        const uint64_t ntx = (gm[1] + out_w - 1) / out_w;
+        const int cands[] = {96, 64, 48, 32, 24};
+        int pick = 0;
+        for (int th : cands) {
+            if (th <= 2 * f->T_ + 4) {
+                continue;
+            }
+            const uint64_t nty = (rows + (th - 2 * f->T_) - 1) / (th - 2 * f->T_);
+            pick = th;
+            if (ntx * nty >= (uint64_t)f->sms_) {
+                break;
+            }
+        }
+        f->TH_ = pick;
+        if (cfg.tile_rows > 2 * f->T_ + 1 && cfg.tile_rows <= 200) {
+            f->TH_ = cfg.tile_rows;
+        }
+    }
+
+    // Device memory.  The 2-D buffers are padded to at least one tile so a TMA box never exceeds
+    // the tensor it reads from.
+    const uint64_t alloc_layers = (n == 2) ? std::max<uint64_t>(f->buf_layers_, 256) : f->buf_layers_;
+    const size_t ubytes = (size_t)alloc_layers * f->layer_floats_ * sizeof(float);
+    const uint64_t mask_rows = (n == 2) ? alloc_layers : alloc_layers * gm[1];
+    const size_t mbytes = (size_t)mask_rows * f->mask_wpr_ * sizeof(uint32_t);
+    bool ok = true;
+    const int nbuf = (n == 2) ? 2 : 1;  // the 3-D sweep runs in place
+    for (int i = 0; i < nbuf && ok; ++i) {
+        ok = cudaMalloc(&f->u_[i], ubytes) == cudaSuccess && cudaMemset(f->u_[i], 0, ubytes) == cudaSuccess;
+    }
+    ok = ok && cudaMalloc(&f->freemask_, mbytes) == cudaSuccess && cudaMemset(f->freemask_, 0, mbytes) == cudaSuccess;
+    ok = ok && cudaMalloc(&f->ctrl_, sizeof(Ctrl)) == cudaSuccess && cudaMemset(f->ctrl_, 0, sizeof(Ctrl)) == cudaSuccess;
+    ok = ok && cudaMallocHost(&f->ctrl_host_, sizeof(Ctrl) * kSlots) == cudaSuccess;
+    if (ok) {
+        memset(f->ctrl_host_, 0, sizeof(Ctrl) * kSlots);
+        f->device_bytes_ = ubytes * nbuf + mbytes + sizeof(Ctrl);
+        if (cfg.use_stream) {
+            f->stream_ = cfg.stream;
+        } else {
+            ok = cudaStreamCreateWithFlags(&f->stream_, cudaStreamNonBlocking) == cudaSuccess;
+            f->own_stream_ = ok;
+        }
+    }
+    for (int i = 0; i < kSlots && ok; ++i) {
+        ok = cudaEventCreateWithFlags(&f->events_[i], cudaEventDisableTiming) == cudaSuccess;
+        f->events_ok_ = ok;
+    }
+    if (!ok) {
+        cudaGetLastError();
+        delete f;
+        return kDeviceMalloc;
+    }
+    if (n == 2) {
+        const int r = f->build_tensor_maps();
+        if (r != kSuccess) {
+            delete f;
+            return r;
+        }
+    }
+    if (cudaDeviceSynchronize() != cudaSuccess) {
+        delete f;
+        return kDeviceSynchronize;
+    }
+    *out = f;
+    return kSuccess;
+}
+
+Field::~Field()
+{
+    if (cfg_.device >= 0) {
+        DeviceGuard guard(cfg_.device);
+        if (stream_ != nullptr || cfg_.use_stream) {
+            cudaStreamSynchronize(stream_);
+        }
+        for (int i = 0; i < 2; ++i) {
+            if (u_[i]) cudaFree(u_[i]);
+        }
+        if (freemask_) cudaFree(freemask_);
+        if (ctrl_) cudaFree(ctrl_);
+        if (ctrl_host_) cudaFreeHost(ctrl_host_);
+        if (staging_) cudaFree(staging_);
+        if (events_ok_) {
+            for (int i = 0; i < kSlots; ++i) cudaEventDestroy(events_[i]);
+        }
+        if (own_stream_) cudaStreamDestroy(stream_);
+    }
+}
+
+int Field::build_tensor_maps()
+{
+    EncodeTiledFn enc = encode_tiled();
+    if (enc == nullptr) {
+        fprintf(stderr, "Error[epic_b200]: cuTensorMapEncodeTiled is not available from the driver.\n");
+        return kInvalidCudaParam;
+    }
+    const uint64_t alloc_layers = std::max<uint64_t>(buf_layers_, 256);
+    for (int i = 0; i < 2; ++i) {
+        cuuint64_t gdim[2] = {(cuuint64_t)pitch_, (cuuint64_t)alloc_layers};
+        cuuint64_t gstride[1] = {(cuuint64_t)pitch_ * sizeof(float)};
+        cuuint32_t box[2] = {(cuuint32_t)kTileW, (cuuint32_t)TH_};
+        cuuint32_t estride[2] = {1, 1};
+        const CUresult r = enc(&tmap_[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, u_[i], gdim, gstride, box, estride,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            fprintf(stderr, "Error[epic_b200]: cuTensorMapEncodeTiled failed (%d).\n", (int)r);
+            return kInvalidCudaParam;
+        }
+    }
+    return kSuccess;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host <-> device
+
+static bool range_ok(int64_t grow0, uint64_t buf_layers, uint64_t first, uint64_t layers)
+{
+    const int64_t b = (int64_t)first - grow0;
+    return layers > 0 && b >= 0 && (uint64_t)b + layers <= buf_layers;
+}
+
+int Field::upload_u(const float *host, uint64_t first, uint64_t layers)
+{
+    if (host == nullptr || !range_ok(grow0_, buf_layers_, first, layers)) {
+        return kInvalidData;
+    }
+    DeviceGuard guard(cfg_.device);
+    const uint64_t inner = gm_[n_ - 1];
+    const uint64_t rows_per_layer = (n_ == 2) ? 1 : gm_[1];
+    float *dst = u_[cur_] + (uint64_t)((int64_t)first - grow0_) * layer_floats_;
+    if (cudaMemcpy2DAsync(dst, pitch_ * sizeof(float), host, inner * sizeof(float), inner * sizeof(float),
+                          layers * rows_per_layer, cudaMemcpyHostToDevice, stream_) != cudaSuccess ||
+        cudaStreamSynchronize(stream_) != cudaSuccess) {
+        cudaGetLastError();
+        return kMemcpyToDevice;
+    }
+    return kSuccess;
+}
+
+int Field::download_u(float *host, uint64_t first, uint64_t layers)
+{
+    if (host == nullptr || !range_ok(grow0_, buf_layers_, first, layers)) {
+        return kInvalidData;
+    }
+    DeviceGuard guard(cfg_.device);
+    const uint64_t inner = gm_[n_ - 1];
+    const uint64_t rows_per_layer = (n_ == 2) ? 1 : gm_[1];
+    const float *src = u_[cur_] + (uint64_t)((int64_t)first - grow0_) * layer_floats_;
+    if (cudaMemcpy2DAsync(host, inner * sizeof(float), src, pitch_ * sizeof(float), inner * sizeof(float),
+                          layers * rows_per_layer, cudaMemcpyDeviceToHost, stream_) != cudaSuccess ||
+        cudaStreamSynchronize(stream_) != cudaSuccess) {
+        cudaGetLastError();
+        return kMemcpyToHost;
+    }
+    return kSuccess;
+}
+
+static int ensure_staging(void **staging, size_t *have, size_t want)
+{
+    if (*have >= want) {
+        return kSuccess;
+    }
+    if (*staging) {
+        cudaFree(*staging);
+        *staging = nullptr;
+        *have = 0;
+    }
+    if (cudaMalloc(staging, want) != cudaSuccess) {
+        cudaGetLastError();
+        return kDeviceMalloc;
+    }
+    *have = want;
+    return kSuccess;
+}
+
+int Field::upload_locked(const uint32_t *host, uint64_t first, uint64_t layers)
+{
+    if (host == nullptr || !range_ok(grow0_, buf_layers_, first, layers)) {
+        return kInvalidData;
+    }
+    DeviceGuard guard(cfg_.device);
+    const uint64_t inner = gm_[n_ - 1];
+    const uint64_t rows_per_layer = (n_ == 2) ? 1 : gm_[1];
+    const uint64_t total_rows = layers * rows_per_layer;
+    const uint64_t row_bytes = inner * sizeof(uint32_t);
+    const uint64_t chunk_rows = std::max<uint64_t>(1, std::min<uint64_t>(total_rows, (64ull << 20) / row_bytes));
+    int r = ensure_staging(&staging_, &staging_bytes_, chunk_rows * row_bytes);
+    if (r != kSuccess) {
+        return r;
+    }
+    const uint64_t mask_row0 = (uint64_t)((int64_t)first - grow0_) * rows_per_layer;
+    for (uint64_t done = 0; done < total_rows; done += chunk_rows) {
+        const uint64_t nrows = std::min(chunk_rows, total_rows - done);
+        if (cudaMemcpyAsync(staging_, host + done * inner, nrows * row_bytes, cudaMemcpyHostToDevice, stream_) !=
+            cudaSuccess) {
+            cudaGetLastError();
+            return kMemcpyToDevice;
+        }
+        const uint64_t warps = nrows * mask_wpr_;
+        const uint64_t blocks = (warps * 32 + 255) / 256;
+        pack_locked_kernel<<<(unsigned)blocks, 256, 0, stream_>>>((const uint32_t *)staging_,
+                                                                   freemask_ + (mask_row0 + done) * mask_wpr_, nrows,
+                                                                   (uint32_t)inner, (uint32_t)mask_wpr_);
+        launches_++;
+        if (cudaGetLastError() != cudaSuccess) {
+            return kKernelExecution;
+        }
+        // the staging buffer is reused by the next chunk: pageable copies are synchronous w.r.t. the
+        // host buffer only, so wait for the pack kernel
+        if (cudaStreamSynchronize(stream_) != cudaSuccess) {
+            return kDeviceSynchronize;
+        }
+    }
+    return kSuccess;
+}
+
+int Field::download_locked(uint32_t *host, uint64_t first, uint64_t layers)
+{
+    if (host == nullptr || !range_ok(grow0_, buf_layers_, first, layers)) {
+        return kInvalidData;
+    }
+    DeviceGuard guard(cfg_.device);
+    const uint64_t inner = gm_[n_ - 1];
+    const uint64_t rows_per_layer = (n_ == 2) ? 1 : gm_[1];
+    const uint64_t total_rows = layers * rows_per_layer;
+    const uint64_t row_bytes = inner * sizeof(uint32_t);
+    const uint64_t chunk_rows = std::max<uint64_t>(1, std::min<uint64_t>(total_rows, (64ull << 20) / row_bytes));
+    int r = ensure_staging(&staging_, &staging_bytes_, chunk_rows * row_bytes);
+    if (r != kSuccess) {
+        return r;
+    }
+    const uint64_t mask_row0 = (uint64_t)((int64_t)first - grow0_) * rows_per_layer;
+    for (uint64_t done = 0; done < total_rows; done += chunk_rows) {
+        const uint64_t nrows = std::min(chunk_rows, total_rows - done);
+        const uint64_t cells = nrows * inner;
+        unpack_locked_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, stream_>>>(
+            freemask_ + (mask_row0 + done) * mask_wpr_, (uint32_t *)staging_, nrows, (uint32_t)inner,
+            (uint32_t)mask_wpr_);
+        launches_++;
+        if (cudaGetLastError() != cudaSuccess) {
+            return kKernelExecution;
+        }
+        if (cudaMemcpyAsync(host + done * inner, staging_, nrows * row_bytes, cudaMemcpyDeviceToHost, stream_) !=
+                cudaSuccess ||
+            cudaStreamSynchronize(stream_) != cudaSuccess) {
+            cudaGetLastError();
+            return kMemcpyToHost;
+        }
+    }
+    return kSuccess;
+}
+
+float *Field::layer_ptr(int64_t layer)
+{
+    const int64_t b = layer - grow0_;
+    if (b < 0 || (uint64_t)b >= buf_layers_) {
+        return nullptr;
+    }
+    return u_[cur_] + (uint64_t)b * layer_floats_;
+}
+
+int Field::sync()
+{
+    DeviceGuard guard(cfg_.device);
+    return cudaStreamSynchronize(stream_) == cudaSuccess ? kSuccess : kDeviceSynchronize;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Sweeps
+
+int Field::launch_pass_2d(uint32_t it0, uint32_t count, bool check_last)
+{
+    Sweep2DParams p;
+    memset(&p, 0, sizeof(p));
+    p.dst = u_[cur_ ^ 1];
+    p.freemask = freemask_;
+    p.ctrl_done = &ctrl_->done;
+    p.delta_bits = &ctrl_->delta_bits;
+    p.pitch = pitch_;
+    p.mask_wpr = (uint32_t)mask_wpr_;
+    p.m0 = (uint32_t)gm_[0];
+    p.m1 = (uint32_t)gm_[1];
+    p.grow0 = (int32_t)grow0_;
+    p.buf_rows = (uint32_t)buf_layers_;
+    p.own_lo = (uint32_t)own_lo_;
+    p.own_hi = (uint32_t)own_hi_;
+    p.TH = (uint32_t)TH_;
+    p.T = (uint32_t)T_;
+    p.HC = 4u * ((p.T + 3u) / 4u);
+    p.out_h = p.TH - 2u * p.T;
+    p.out_w = kTileW - 2u * p.HC;
+    p.ntx = (uint32_t)((gm_[1] + p.out_w - 1) / p.out_w);
+    const uint32_t nty = (uint32_t)((rows_ + p.out_h - 1) / p.out_h);
+    p.count = count;
+    p.parity0 = (uint32_t)(((int64_t)it0 + grow0_) & 1);
+    p.check = check_last ? 1u : 0u;
+    const size_t smem = sweep2d_smem_bytes(p.TH, 256);
+    const uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(2, (227 * 1024) / (smem + 1024)));
+    p.prefetch_stride = per_sm * (uint32_t)sms_;
+    const uint32_t grid = p.ntx * nty;
+
+    if (!attr_done_) {  // per device, so per field
+        if (!allow_smem(sweep2d_kernel<StrictMath, 256>, 227 * 1024) ||
+            !allow_smem(sweep2d_kernel<FastMath, 256>, 227 * 1024)) {
+            cudaGetLastError();
+            return kInvalidCudaParam;
+        }
+        attr_done_ = true;
+    }
+    if (cfg_.math == MATH_STRICT) {
+        StrictMath m;
+        m.t = nullptr;
+        m.log2n = kLog4;
+        sweep2d_kernel<StrictMath, 256><<<grid, 256, smem, stream_>>>(tmap_[cur_], p, m);
+    } else {
+        FastMath m;
+        m.ln2n = 1.3862943611198906f;
+        sweep2d_kernel<FastMath, 256><<<grid, 256, smem, stream_>>>(tmap_[cur_], p, m);
+    }
+    launches_++;
+    if (cudaGetLastError() != cudaSuccess) {
+        return kKernelExecution;
+    }
+    cur_ ^= 1;
+    return kSuccess;
+}
+
+int Field::launch_pass_3d(uint32_t it0, uint32_t count, bool check_last)
+{
+    for (uint32_t s = 0; s < count; ++s) {
+        Sweep3DParams p;
+        memset(&p, 0, sizeof(p));
+        p.u = u_[cur_];
+        p.freemask = freemask_;
+        p.ctrl_done = &ctrl_->done;
+        p.delta_bits = &ctrl_->delta_bits;
+        p.pitch = pitch_;
+        p.layer_floats = layer_floats_;
+        p.mask_wpr = (uint32_t)mask_wpr_;
+        p.m0 = (uint32_t)gm_[0];
+        p.m1 = (uint32_t)gm_[1];
+        p.m2 = (uint32_t)gm_[2];
+        p.grow0 = grow0_;
+        p.own_lo = (uint32_t)own_lo_;
+        p.own_hi = (uint32_t)own_hi_;
+        p.segs = (uint32_t)((pitch_ + 127) / 128);
+        p.row_blocks = (uint32_t)((gm_[1] + 7) / 8);
+        p.it = it0 + s;
+        p.check = (check_last && s + 1 == count) ? 1u : 0u;
+        const uint64_t work = (uint64_t)rows_ * p.row_blocks * p.segs;
+        const uint32_t grid = (uint32_t)std::min<uint64_t>(work, (uint64_t)sms_ * 3);
+        if (cfg_.math == MATH_STRICT) {
+            StrictMath m;
+            m.t = nullptr;
+            m.log2n = kLog6;
+            sweep3d_kernel<StrictMath><<<grid, 256, 0, stream_>>>(p, m);
+        } else {
+            FastMath m;
+            m.ln2n = 1.791759469228055f;
+            sweep3d_kernel<FastMath><<<grid, 256, 0, stream_>>>(p, m);
+        }
+        launches_++;
+        if (cudaGetLastError() != cudaSuccess) {
+            return kKernelExecution;
+        }
+    }
+    return kSuccess;
+}
+
+int Field::launch_pass(uint32_t it0, uint32_t count, bool check_last)
+{
+    return (n_ == 2) ? launch_pass_2d(it0, count, check_last) : launch_pass_3d(it0, count, check_last);
+}
+
+int Field::run(uint32_t it0, uint32_t count, bool check_last)
+{
+    DeviceGuard guard(cfg_.device);
+    uint32_t done = 0;
+    while (done < count) {
+        const uint32_t c = std::min<uint32_t>((uint32_t)T_, count - done);
+        const int r = launch_pass(it0 + done, c, check_last && (done + c == count));
+        if (r != kSuccess) {
+            return r;
+        }
+        done += c;
+    }
+    return kSuccess;
+}
+
+int Field::read_delta(float *delta)
+{
+    DeviceGuard guard(cfg_.device);
+    take_delta_kernel<<<1, 1, 0, stream_>>>(ctrl_, 0);
+    launches_++;
+    if (cudaGetLastError() != cudaSuccess) {
+        return kKernelExecution;
+    }
+    if (cudaMemcpyAsync(&ctrl_host_[0], ctrl_, sizeof(Ctrl), cudaMemcpyDeviceToHost, stream_) != cudaSuccess) {
+        cudaGetLastError();
+        return kMemcpyToHost;
+    }
+    if (cudaStreamSynchronize(stream_) != cudaSuccess) {
+        cudaGetLastError();
+        return kDeviceSynchronize;
+    }
+    *delta = ctrl_host_[0].last_delta;
+    return kSuccess;
+}
+
+int Field::solve(float epsilon, uint32_t stagger, uint32_t m_max, uint32_t *iteration, float *delta)
+{
+    if (!(epsilon > 0.0f) || stagger == 0 || iteration == nullptr || delta == nullptr) {
+        return kInvalidData;
+    }
+    DeviceGuard guard(cfg_.device);
+    if (cudaMemsetAsync(ctrl_, 0, sizeof(Ctrl), stream_) != cudaSuccess) {
+        cudaGetLastError();
+        return kMemcpyToDevice;
+    }
+    // Period 0 is the check sweep at iteration 0; period k >= 1 covers iterations
+    // (k-1)*stagger+1 .. k*stagger and ends with the check sweep at k*stagger
+    // (reference harmonic_gpu.cu:266-282).  Two periods are kept in flight.
+    uint64_t it = 0;
+    const Ctrl *fin = nullptr;
+    for (uint64_t period = 0; fin == nullptr; ++period) {
+        if (period >= 2) {
+            const int slot = (int)((period - 2) % kSlots);
+            if (cudaEventSynchronize(events_[slot]) != cudaSuccess) {
+                cudaGetLastError();
+                return kDeviceSynchronize;
+            }
+            if (ctrl_host_[slot].done) {
+                fin = &ctrl_host_[slot];
+                break;
+            }
+        }
+        const uint32_t count = (period == 0) ? 1u : stagger;
+        if (it + count > 0xffffffffull) {
+            return kInvalidData;  // the reference's 32-bit iteration counter would wrap
+        }
+        int r = run((uint32_t)it, count, true);
+        if (r != kSuccess) {
+            return r;
+        }
+        it += count;
+        const int slot = (int)(period % kSlots);
+        decide_kernel<<<1, 1, 0, stream_>>>(ctrl_, epsilon, (uint32_t)it, m_max, (uint32_t)cur_);
+        launches_++;
+        if (cudaGetLastError() != cudaSuccess) {
+            return kKernelExecution;
+        }
+        if (cudaMemcpyAsync(&ctrl_host_[slot], ctrl_, sizeof(Ctrl), cudaMemcpyDeviceToHost, stream_) != cudaSuccess ||
+            cudaEventRecord(events_[slot], stream_) != cudaSuccess) {
+            cudaGetLastError();
+            return kMemcpyToHost;
+        }
+    }
+    if (cudaStreamSynchronize(stream_) != cudaSuccess) {
+        cudaGetLastError();
+        return kDeviceSynchronize;
+    }
+    cur_ = (int)fin->final_buffer;
+    *iteration = fin->final_iteration;
+    *delta = fin->last_delta;
+    // leave the flag clear so that later update / update_and_check calls sweep again
+    if (cudaMemsetAsync(ctrl_, 0, sizeof(Ctrl), stream_) != cudaSuccess || cudaStreamSynchronize(stream_) != cudaSuccess) {
+        cudaGetLastError();
+        return kDeviceSynchronize;
+    }
+    return kSuccess;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Sparse edits
+
+int Field::set_cells_2d(uint32_t k, const uint32_t *v, const uint32_t *types)
+{
+    if (n_ != 2 || k == 0 || v == nullptr || types == nullptr) {
+        return kInvalidData;
+    }
+    DeviceGuard guard(cfg_.device);
+    // The reference's CPU twin applies the edits in order; when a cell appears more than once the
+    // last edit wins.  last[i] = index of the last *valid* edit of the cell edit i targets.
+    std::vector<uint32_t> last(k);
+    {
+        std::unordered_map<uint64_t, uint32_t> winner;
+        winner.reserve((size_t)k * 2);
+        for (uint32_t i = 0; i < k; ++i) {
+            const uint32_t x = v[2 * i], y = v[2 * i + 1];
+            if (x < gm_[1] && y < gm_[0] && types[i] <= 2u) {
+                winner[((uint64_t)y << 32) | x] = i;
+            }
+        }
+        for (uint32_t i = 0; i < k; ++i) {
+            auto itw = winner.find(((uint64_t)v[2 * i + 1] << 32) | v[2 * i]);
+            last[i] = (itw == winner.end()) ? i : itw->second;
+        }
+    }
+    const size_t bytes = (size_t)k * 4 * sizeof(uint32_t);
+    int r = ensure_staging(&staging_, &staging_bytes_, bytes);
+    if (r != kSuccess) {
+        return r;
+    }
+    uint32_t *d_v = (uint32_t *)staging_;
+    uint32_t *d_types = d_v + 2 * (size_t)k;
+    uint32_t *d_last = d_types + k;
+    if (cudaMemcpyAsync(d_v, v, (size_t)k * 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, stream_) != cudaSuccess ||
+        cudaMemcpyAsync(d_types, types, (size_t)k * sizeof(uint32_t), cudaMemcpyHostToDevice, stream_) != cudaSuccess ||
+        cudaMemcpyAsync(d_last, last.data(), (size_t)k * sizeof(uint32_t), cudaMemcpyHostToDevice, stream_) !=
+            cudaSuccess) {
+        cudaGetLastError();
+        return kMemcpyToDevice;
+    }
+    set_cells_2d_kernel<<<(k + 255) / 256, 256, 0, stream_>>>(u_[cur_], freemask_, pitch_, (uint32_t)mask_wpr_,
+                                                             (uint32_t)gm_[0], (uint32_t)gm_[1], grow0_,
+                                                             (uint32_t)buf_layers_, k, d_v, d_types, d_last);
+    launches_++;
+    if (cudaGetLastError() != cudaSuccess) {
+        return kKernelExecution;
+    }
+    if (cudaStreamSynchronize(stream_) != cudaSuccess) {
+        cudaGetLastError();
+        return kDeviceSynchronize;
+    }
+    return kSuccess;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Streamlines
+
+static FieldView2D make_view(const float *u, const uint32_t *mask, uint64_t pitch, uint64_t mask_wpr,
+                             const uint64_t *gm, int64_t grow0)
+{
+    FieldView2D f;
+    f.u = u;
+    f.mask = mask;
+    f.pitch = pitch;
+    f.mask_wpr = (uint32_t)mask_wpr;
+    f.m0 = (uint32_t)gm[0];
+    f.m1 = (uint32_t)gm[1];
+    f.grow0 = grow0;
+    return f;
+}
+
+int Field::potential_2d(float x, float y, float *value)
+{
+    if (n_ != 2 || value == nullptr || rows_ != gm_[0]) {
+        return kInvalidData;
+    }
+    DeviceGuard guard(cfg_.device);
+    int r = ensure_staging(&staging_, &staging_bytes_, 64);
+    if (r != kSuccess) {
+        return r;
+    }
+    float *d_out = (float *)staging_;
+    int *d_ret = (int *)(d_out + 2);
+    potential_gradient_kernel<<<1, 1, 0, stream_>>>(make_view(u_[cur_], freemask_, pitch_, mask_wpr_, gm_, grow0_), x, y,
+                                                    0.0f, 0, d_out, d_ret);
+    launches_++;
+    float h[3];
+    if (cudaGetLastError() != cudaSuccess) {
+        return kKernelExecution;
+    }
+    if (cudaMemcpyAsync(h, staging_, 12, cudaMemcpyDeviceToHost, stream_) != cudaSuccess ||
+        cudaStreamSynchronize(stream_) != cudaSuccess) {
+        cudaGetLastError();
+        return kMemcpyToHost;
+    }
+    int ret;
+    memcpy(&ret, &h[2], 4);
+    if (ret == kSuccess) {
+        *value = h[0];
+    }
+    return ret;
+}
+
+int Field::gradient_2d(float x, float y, float cd, float *px, float *py)
+{
+    if (n_ != 2 || px == nullptr || py == nullptr || rows_ != gm_[0]) {
+        return kInvalidData;
+    }
+    DeviceGuard guard(cfg_.device);
+    int r = ensure_staging(&staging_, &staging_bytes_, 64);
+    if (r != kSuccess) {
+        return r;
+    }
+    float *d_out = (float *)staging_;
+    int *d_ret = (int *)(d_out + 2);
+    potential_gradient_kernel<<<1, 1, 0, stream_>>>(make_view(u_[cur_], freemask_, pitch_, mask_wpr_, gm_, grow0_), x, y,
+                                                    cd, 1, d_out, d_ret);
+    launches_++;
+    float h[3];
+    if (cudaGetLastError() != cudaSuccess) {
+        return kKernelExecution;
+    }
+    if (cudaMemcpyAsync(h, staging_, 12, cudaMemcpyDeviceToHost, stream_) != cudaSuccess ||
+        cudaStreamSynchronize(stream_) != cudaSuccess) {
+        cudaGetLastError();
+        return kMemcpyToHost;
+    }
+    int ret;
+    memcpy(&ret, &h[2], 4);
+    if (ret == kSuccess) {
+        *px = h[0];
+        *py = h[1];
+    }
+    return ret;
+}
+
+int Field::paths_2d(uint32_t count, const float *starts, float step, float cd, uint32_t max_length, int *ret,
+                    uint32_t *k, float **paths)
+{
+    if (n_ != 2 || count == 0 || starts == nullptr || ret == nullptr || k == nullptr || paths == nullptr ||
+        rows_ != gm_[0]) {
+        return kInvalidData;
+    }
+    DeviceGuard guard(cfg_.device);
+    // chunk: points emitted per path and launch
+    const uint32_t chunk = (uint32_t)std::max<uint64_t>(256, std::min<uint64_t>(65536, (32ull << 20) / ((uint64_t)count * 8)));
+    const size_t out_bytes = (size_t)count * chunk * 2 * sizeof(float);
+    const size_t st_bytes = round_up((size_t)count * sizeof(PathState), 256);
+    const size_t em_bytes = round_up((size_t)count * sizeof(uint32_t), 256);
+    const size_t in_bytes = round_up((size_t)count * 2 * sizeof(float), 256);
+    unsigned char *base = nullptr;
+    if (cudaMalloc(&base, out_bytes + st_bytes + em_bytes + in_bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return kDeviceMalloc;
+    }
+    float *d_out = (float *)base;
+    PathState *d_states = (PathState *)(base + out_bytes);
+    uint32_t *d_emitted = (uint32_t *)(base + out_bytes + st_bytes);
+    float *d_starts = (float *)(base + out_bytes + st_bytes + em_bytes);
+    int result = kSuccess;
+    std::vector<std::vector<float>> acc(count);
+    std::vector<uint32_t> emitted(count);
+    std::vector<PathState> states(count);
+    std::vector<float> chunk_host;
+    // `pathVector.size() < 2 * maxLength` is evaluated in 32-bit unsigned arithmetic by the reference
+    // (harmonic_path_cpu.cpp:187), so the product wraps.
+    const uint64_t max_floats = (uint64_t)(uint32_t)(2u * max_length);
+    if (cudaMemcpyAsync(d_starts, starts, (size_t)count * 2 * sizeof(float), cudaMemcpyHostToDevice, stream_) !=
+        cudaSuccess) {
+        cudaGetLastError();
+        result = kMemcpyToDevice;
+    }
+    const FieldView2D view = make_view(u_[cur_], freemask_, pitch_, mask_wpr_, gm_, grow0_);
+    bool running = true;
+    for (uint32_t launch = 0; running && result == kSuccess; ++launch) {
+        path_2d_kernel<<<(count + 31) / 32, 32, 0, stream_>>>(view, count, d_starts, step, cd, max_floats, chunk,
+                                                              d_states, d_out, d_emitted, launch == 0 ? 1u : 0u);
+        launches_++;
+        if (cudaGetLastError() != cudaSuccess) {
+            result = kKernelExecution;
+            break;
+        }
+        if (cudaMemcpyAsync(emitted.data(), d_emitted, (size_t)count * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                            stream_) != cudaSuccess ||
+            cudaMemcpyAsync(states.data(), d_states, (size_t)count * sizeof(PathState), cudaMemcpyDeviceToHost,
+                            stream_) != cudaSuccess ||
+            cudaStreamSynchronize(stream_) != cudaSuccess) {
+            cudaGetLastError();
+            result = kMemcpyToHost;
+            break;
+        }
+        running = false;
+        for (uint32_t i = 0; i < count; ++i) {
+            if (emitted[i] > 0) {
+                const size_t old = acc[i].size();
+                acc[i].resize(old + (size_t)emitted[i] * 2);
+                if (cudaMemcpy(acc[i].data() + old, d_out + (size_t)i * chunk * 2, (size_t)emitted[i] * 2 * sizeof(float),
+                               cudaMemcpyDeviceToHost) != cudaSuccess) {
+                    cudaGetLastError();
+                    result = kMemcpyToHost;
+                }
+            }
+            if (states[i].status == -1) {
+                running = true;
+            }
+        }
+    }
+    cudaFree(base);
+    if (result != kSuccess) {
+        return result;
+    }
+    for (uint32_t i = 0; i < count; ++i) {
+        ret[i] = states[i].status;
+        k[i] = 0;
+        paths[i] = nullptr;
+        if (states[i].status == kSuccess) {
+            k[i] = (uint32_t)(acc[i].size() / 2);
+            paths[i] = new float[acc[i].size()];   // released by the caller with delete[]
+            memcpy(paths[i], acc[i].data(), acc[i].size() * sizeof(float));
+        }
+    }
+    return kSuccess;
+}
+
+}  // namespace epic_b200

@@ -1,0 +1,139 @@
+// field.h -- device residency and sweep scheduling for one slab of a harmonic grid.
+//
+// A `Field` owns everything the reference keeps behind `Harmonic::d_m/d_u/d_locked/d_delta`
+// (reference libepic/src/harmonic/harmonic_model_gpu.cu:34-204, harmonic_gpu.cu:205-223) for
+// the x0-range [row0, row0+rows) of a grid, laid out for B200:
+//
+//   u[2]      two ping-pong buffers of (rows + 2*ghost) x0-layers, each innermost row padded to a
+//             128-byte multiple ("pitch"); a pass reads one and writes the other, so tiles can
+//             re-read their halos while their neighbours are being written.
+//   freemask  1 bit per cell, 1 = the cell is not locked.  1/32 of the traffic of the reference's
+//             uint32 `locked` array.  (The sweep additionally never touches the global border.)
+//   ctrl      a few words of device state: the max-delta accumulator, the convergence flag that
+//             lets already-queued passes retire as no-ops, the final iteration count.
+//
+// A "pass" is one kernel launch that performs up to T consecutive red-black half-sweeps on every
+// tile in shared memory (temporal blocking).  `run()` cuts any iteration range into passes so that
+// a convergence-check sweep is always the last sweep of its pass; `solve()` is the reference's
+// harmonic_execute_gpu loop (harmonic_gpu.cu:226-305) with the checks decided on the device and
+// read back asynchronously.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace epic_b200 {
+
+enum MathMode { MATH_STRICT = 0, MATH_FAST = 1 };
+
+struct Ctrl;
+
+struct FieldConfig {
+    int device = -1;          // -1 = the current device
+    MathMode math = MATH_STRICT;
+    int sweeps_per_pass = 0;  // T; 0 = default
+    int tile_rows = 0;        // 2-D: rows of the shared-memory tile (incl. halo); 0 = by grid size
+    cudaStream_t stream = nullptr;  // run on this stream instead of a private one
+    bool use_stream = false;
+};
+
+// Return codes are the reference's (libepic/include/epic/error_codes.h:31-46).
+class Field {
+public:
+    // n = 2 or 3; gm = global dimensions; this slab owns x0 in [row0, row0+rows).
+    // `ghost` x0-layers are kept on each side for neighbouring slabs (0 for a whole grid).
+    static int create(Field **out, unsigned n, const uint64_t *gm, uint64_t row0, uint64_t rows,
+                      unsigned ghost, const FieldConfig &cfg);
+    ~Field();
+
+    // Host <-> device.  Host arrays are dense; `layers` x0-layers starting at global layer `first`
+    // (must lie inside the owned + ghost range).  All four are complete on return.
+    int upload_u(const float *host, uint64_t first, uint64_t layers);
+    int upload_locked(const uint32_t *host, uint64_t first, uint64_t layers);
+    int download_u(float *host, uint64_t first, uint64_t layers);
+    int download_locked(uint32_t *host, uint64_t first, uint64_t layers);
+
+    // `count` half-sweeps starting at iteration `it0`, enqueued on the stream (no sync).  If
+    // `check_last`, the last one accumulates delta; fetch it with read_delta().
+    int run(uint32_t it0, uint32_t count, bool check_last);
+    // Fetch (and reset) the delta accumulated by the last check sweep; syncs the stream.
+    int read_delta(float *delta);
+
+    // The reference's execute loop: iterate from iteration 0 until a check sweep sees
+    // delta < epsilon with currentIteration >= m_max.  Outputs the final iteration and delta.
+    int solve(float epsilon, uint32_t stagger, uint32_t m_max, uint32_t *iteration, float *delta);
+
+    // k sparse edits (x = column, y = global row), types 0 goal / 1 obstacle / 2 free.
+    int set_cells_2d(uint32_t k, const uint32_t *v, const uint32_t *types);
+
+    // Streamlines on the device-resident field (2-D fields holding the rows the path visits).
+    // Same arithmetic, operation for operation, as the reference's CPU functions.
+    int potential_2d(float x, float y, float *value);
+    int gradient_2d(float x, float y, float cd, float *px, float *py);
+    // `count` paths in one go; ret[i], k[i] per path; paths[i] = new float[2*k[i]] (or nullptr).
+    int paths_2d(uint32_t count, const float *starts, float step, float cd, uint32_t max_length,
+                 int *ret, uint32_t *k, float **paths);
+
+    // Ghost-layer plumbing for sharded runs: device pointer into the CURRENT buffer at global
+    // layer `layer` (owned or ghost).
+    float *layer_ptr(int64_t layer);
+
+    int sync();
+    cudaStream_t stream() const { return stream_; }
+    int sweeps_per_pass() const { return T_; }
+    uint64_t pitch() const { return pitch_; }
+    uint64_t layer_floats() const { return layer_floats_; }
+    unsigned dims() const { return n_; }
+    const uint64_t *global_dims() const { return gm_; }
+    uint64_t rows() const { return rows_; }
+    uint64_t row0() const { return row0_; }
+    unsigned ghost() const { return ghost_; }
+    MathMode math() const { return cfg_.math; }
+    int device() const { return cfg_.device; }
+    uint64_t launches() const { return launches_; }
+    int tile_rows() const { return TH_; }
+    size_t device_bytes() const { return device_bytes_; }
+
+private:
+    Field() {}
+    int build_tensor_maps();
+    int launch_pass(uint32_t it0, uint32_t count, bool check_last);
+    int launch_pass_2d(uint32_t it0, uint32_t count, bool check_last);
+    int launch_pass_3d(uint32_t it0, uint32_t count, bool check_last);
+
+    FieldConfig cfg_;
+    unsigned n_ = 0;
+    uint64_t gm_[3] = {1, 1, 1};
+    uint64_t row0_ = 0, rows_ = 0;
+    unsigned ghost_ = 0;
+    int64_t grow0_ = 0;          // global layer of buffer layer 0 (= row0 - ghost, may be negative)
+    uint64_t pitch_ = 0;         // floats per innermost row
+    uint64_t layer_floats_ = 0;  // floats per x0-layer (2-D: pitch; 3-D: m1 * pitch)
+    uint64_t buf_layers_ = 0;    // owned + 2*ghost
+    uint64_t own_lo_ = 0, own_hi_ = 0;  // buffer layers written by this slab
+    float *u_[2] = {nullptr, nullptr};
+    int cur_ = 0;
+    uint32_t *freemask_ = nullptr;
+    uint64_t mask_wpr_ = 0;      // mask words per innermost row
+    Ctrl *ctrl_ = nullptr;       // device
+    Ctrl *ctrl_host_ = nullptr;  // pinned ring of slots
+    static const int kSlots = 4;
+    cudaEvent_t events_[kSlots];
+    bool events_ok_ = false;
+    cudaStream_t stream_ = nullptr;
+    bool own_stream_ = false;
+    CUtensorMap tmap_[2];
+    int T_ = 4, TH_ = 96, NT_ = 256;
+    int sms_ = 148;
+    uint64_t launches_ = 0;
+    bool attr_done_ = false;
+    size_t device_bytes_ = 0;
+    void *staging_ = nullptr;    // device scratch for upload_locked / download_locked
+    size_t staging_bytes_ = 0;
+};
+
+// Parses EPIC_MATH (strict|fast), EPIC_SWEEPS_PER_PASS, EPIC_TILE_ROWS, EPIC_DEVICE.
+FieldConfig config_from_env();
+
+}  // namespace epic_b200

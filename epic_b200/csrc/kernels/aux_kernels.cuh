@@ -1,0 +1,300 @@
+// aux_kernels.cuh -- the small kernels around the sweep: locked-array packing, sparse cell edits,
+// the device-side termination rule, and streamline extraction on the device-resident field.
+//
+// Reference behaviour replaced here:
+//   pack_locked_kernel   the 4-byte-per-cell d_locked array of harmonic_model_gpu.cu:124-160 becomes
+//                        1 bit per cell ("free" = locked word is zero)
+//   set_cells_2d_kernel  harmonic_utilities_set_cells_2d_gpu (harmonic_utilities_gpu.cu:38-63)
+//   decide_kernel        the host-side `delta < epsilon` test and loop condition of
+//                        harmonic_execute_gpu (harmonic_gpu.cu:266-290, :409-413), moved onto the device
+//                        so that queued passes retire as no-ops once the rule is met
+//   path kernels         harmonic_compute_{potential,gradient,path}_2d_cpu
+//                        (harmonic_path_cpu.cpp:41-221), same float operations in the same order; this
+//                        translation unit is compiled with -fmad=false so no multiply-add is fused.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace epic_b200 {
+
+struct Ctrl {                      // device-resident control block
+    uint32_t delta_bits;           // running max |du| of the current check sweep (float bits, >= 0)
+    uint32_t done;                 // 1 once a check sweep met the termination rule
+    uint32_t final_iteration;      // currentIteration when `done` was raised
+    uint32_t final_buffer;         // which ping-pong buffer holds the field of that moment
+    float last_delta;              // delta of the most recent check sweep
+    uint32_t last_check_iteration; // currentIteration right after that sweep
+    uint32_t checks;               // number of check sweeps decided so far
+    uint32_t pad;
+};
+
+// One warp packs 32 consecutive cells of one row into one mask word (ballot), coalesced reads.
+// `locked` holds `rows` dense rows of m1 words; mask rows start at `mask` (already offset).
+__global__ void pack_locked_kernel(const uint32_t *__restrict__ locked, uint32_t *__restrict__ mask,
+                                   uint64_t rows, uint32_t m1, uint32_t mask_wpr)
+{
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t total = rows * mask_wpr;
+    if (warp >= total) {
+        return;
+    }
+    const uint64_t row = warp / mask_wpr;
+    const uint32_t w = (uint32_t)(warp % mask_wpr);
+    const uint32_t x = w * 32u + lane;
+    const bool is_free = (x < m1) && (__ldg(locked + row * m1 + x) == 0u);
+    const uint32_t bits = __ballot_sync(0xffffffffu, is_free);
+    if (lane == 0) {
+        mask[row * mask_wpr + w] = bits;
+    }
+}
+
+// Inverse of the above, for download_locked (tests, checkpointing): 1 = locked.
+__global__ void unpack_locked_kernel(const uint32_t *__restrict__ mask, uint32_t *__restrict__ locked,
+                                     uint64_t rows, uint32_t m1, uint32_t mask_wpr)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * m1) {
+        return;
+    }
+    const uint64_t row = i / m1;
+    const uint32_t x = (uint32_t)(i % m1);
+    const uint32_t w = __ldg(mask + row * mask_wpr + (x >> 5));
+    locked[i] = ((w >> (x & 31u)) & 1u) ? 0u : 1u;
+}
+
+// k edits; v = [x0, y0, x1, y1, ...] with x = column, y = global row.  Rows outside
+// [grow_lo, grow_hi) belong to another slab; out-of-range cells and unknown types are skipped.
+// Edits are applied one after the other by a single thread per *cell chain*: the reference's CPU
+// twin applies them in order (harmonic_utilities_cpu.cpp:47-73), so when the same cell appears twice
+// the last edit must win.  Thread i therefore skips its edit when a later edit targets the same cell.
+__global__ void set_cells_2d_kernel(float *__restrict__ u, uint32_t *__restrict__ mask, uint64_t pitch,
+                                    uint32_t mask_wpr, uint32_t m0, uint32_t m1, int64_t grow0,
+                                    uint32_t buf_rows, uint32_t k, const uint32_t *__restrict__ v,
+                                    const uint32_t *__restrict__ types, const uint32_t *__restrict__ last_writer)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= k) {
+        return;
+    }
+    if (last_writer[i] != i) {
+        return;
+    }
+    const uint32_t x = v[2 * i], y = v[2 * i + 1], type = types[i];
+    if (x >= m1 || y >= m0 || type > 2u) {
+        return;
+    }
+    const int64_t b = (int64_t)y - grow0;
+    if (b < 0 || b >= (int64_t)buf_rows) {
+        return;
+    }
+    u[(uint64_t)b * pitch + x] = (type == 0u) ? 0.0f : -1e6f;
+    uint32_t *word = mask + (uint64_t)b * mask_wpr + (x >> 5);
+    const uint32_t bit = 1u << (x & 31u);
+    if (type == 2u) {
+        atomicOr(word, bit);
+    } else {
+        atomicAnd(word, ~bit);
+    }
+}
+
+// The termination rule of harmonic_execute_gpu, evaluated right after a check sweep.
+// `it_after` = currentIteration after that sweep; `buffer` = ping-pong index that now holds the field.
+__global__ void decide_kernel(Ctrl *ctrl, float epsilon, uint32_t it_after, uint32_t m_max, uint32_t buffer)
+{
+    if (ctrl->done) {
+        return;
+    }
+    const float delta = __uint_as_float(ctrl->delta_bits);
+    ctrl->delta_bits = 0u;
+    ctrl->last_delta = delta;
+    ctrl->last_check_iteration = it_after;
+    ctrl->checks += 1u;
+    if (delta < epsilon && it_after >= m_max) {
+        ctrl->final_iteration = it_after;
+        ctrl->final_buffer = buffer;
+        __threadfence();
+        ctrl->done = 1u;
+    }
+}
+
+// Fetch-and-reset of the delta accumulator for single update_and_check calls.
+__global__ void take_delta_kernel(Ctrl *ctrl, uint32_t it_after)
+{
+    ctrl->last_delta = __uint_as_float(ctrl->delta_bits);
+    ctrl->delta_bits = 0u;
+    ctrl->last_check_iteration = it_after;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Streamlines
+
+struct FieldView2D {
+    const float *u;        // current buffer, buffer-row 0
+    const uint32_t *mask;  // free bits, buffer layout
+    uint64_t pitch;
+    uint32_t mask_wpr;
+    uint32_t m0, m1;       // global dimensions
+    int64_t grow0;         // global row of buffer row 0 (0 for a whole-grid field)
+};
+
+enum { kPathOk = 0, kPathInvalidLocation = 10, kPathInvalidGradient = 12, kPathInvalidPath = 13 };
+
+// (unsigned int)f as x86-64 gcc evaluates it: truncate to a signed 64-bit integer, keep the low word.
+__device__ __forceinline__ uint32_t f2u_x86(float f)
+{
+    return (uint32_t)(uint64_t)__float2ll_rz(f);
+}
+
+__device__ __forceinline__ bool cell_locked(const FieldView2D &f, uint32_t xc, uint32_t yc)
+{
+    const uint64_t b = (uint64_t)((int64_t)yc - f.grow0);
+    return ((__ldg(f.mask + b * f.mask_wpr + (xc >> 5)) >> (xc & 31u)) & 1u) == 0u;
+}
+
+__device__ __forceinline__ float cell_u(const FieldView2D &f, uint32_t xc, uint32_t yc)
+{
+    const uint64_t b = (uint64_t)((int64_t)yc - f.grow0);
+    return __ldg(f.u + b * f.pitch + xc);
+}
+
+// harmonic_path_cpu.cpp:52-58 / :168-175: outside the grid, or an obstacle (locked and negative).
+__device__ __forceinline__ bool cell_blocked(const FieldView2D &f, uint32_t xc, uint32_t yc)
+{
+    if (xc >= f.m1 || yc >= f.m0) {
+        return true;
+    }
+    return cell_locked(f, xc, yc) && cell_u(f, xc, yc) < 0.0f;
+}
+
+__device__ int potential_2d(const FieldView2D &f, float x, float y, float *out)
+{
+    if (cell_blocked(f, f2u_x86(__fadd_rn(x, 0.5f)), f2u_x86(__fadd_rn(y, 0.5f)))) {
+        return kPathInvalidLocation;
+    }
+    const uint32_t xl = f2u_x86(__fsub_rn(x, 0.5f)), xr = f2u_x86(__fadd_rn(x, 0.5f));
+    const uint32_t yt = f2u_x86(__fsub_rn(y, 0.5f)), yb = f2u_x86(__fadd_rn(y, 0.5f));
+    if (xl >= f.m1 || xr >= f.m1 || yt >= f.m0 || yb >= f.m0) {
+        return kPathInvalidLocation;  // the reference would read outside the arrays here
+    }
+    const float alpha = __fsub_rn(x, (float)xl);
+    const float beta = __fsub_rn(y, (float)yt);
+    const float na = __fsub_rn(1.0f, alpha), nb = __fsub_rn(1.0f, beta);
+    const float one = __fadd_rn(__fmul_rn(na, cell_u(f, xl, yt)), __fmul_rn(alpha, cell_u(f, xr, yt)));
+    const float two = __fadd_rn(__fmul_rn(na, cell_u(f, xl, yb)), __fmul_rn(alpha, cell_u(f, xr, yb)));
+    *out = __fadd_rn(__fmul_rn(nb, one), __fmul_rn(beta, two));
+    return kPathOk;
+}
+
+__device__ int gradient_2d(const FieldView2D &f, float x, float y, float cd, float *px, float *py)
+{
+    float v0 = 0.0f, v1 = 0.0f, v2 = 0.0f, v3 = 0.0f;
+    int r = potential_2d(f, __fsub_rn(x, cd), y, &v0);
+    r += potential_2d(f, __fadd_rn(x, cd), y, &v1);
+    r += potential_2d(f, x, __fsub_rn(y, cd), &v2);
+    r += potential_2d(f, x, __fadd_rn(y, cd), &v3);
+    if (r != kPathOk) {
+        return kPathInvalidGradient;
+    }
+    const float two_cd = __fmul_rn(2.0f, cd);
+    float gx = __fdiv_rn(__fsub_rn(v1, v0), two_cd);
+    float gy = __fdiv_rn(__fsub_rn(v3, v2), two_cd);
+    const double dx = (double)gx, dy = (double)gy;
+    const float denom = __double2float_rn(__dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy))));
+    *px = __fdiv_rn(gx, denom);
+    *py = __fdiv_rn(gy, denom);
+    return kPathOk;
+}
+
+struct PathState {        // lets a long path continue across launches
+    float x, y;
+    float hx[5], hy[5];   // the previous points, most recent first
+    uint32_t nhist;       // valid entries in hx/hy
+    uint32_t points;      // points emitted so far (including the start)
+    int status;           // -1 running, otherwise the final return code
+};
+
+// One thread per path.  Emits up to `chunk` further points into out[path * chunk * 2 ...] and
+// returns; the host relaunches while any path is still running.  `points` counts over all launches.
+__global__ void path_2d_kernel(FieldView2D f, uint32_t count, const float *__restrict__ starts, float step,
+                               float cd, uint64_t max_floats, uint32_t chunk, PathState *states,
+                               float *__restrict__ out, uint32_t *__restrict__ emitted, uint32_t first_launch)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) {
+        return;
+    }
+    PathState s;
+    float *o = out + (uint64_t)i * chunk * 2;
+    uint32_t n = 0;
+    if (first_launch) {
+        s.x = starts[2 * i];
+        s.y = starts[2 * i + 1];
+        s.nhist = 0;
+        s.points = 0;
+        s.status = -1;
+        if (cell_blocked(f, f2u_x86(__fadd_rn(s.x, 0.5f)), f2u_x86(__fadd_rn(s.y, 0.5f)))) {
+            s.status = kPathInvalidLocation;
+        } else {
+            o[0] = s.x;
+            o[1] = s.y;
+            n = 1;
+            s.points = 1;
+        }
+    } else {
+        s = states[i];
+    }
+    const float half_step = __fdiv_rn(step, 2.0f);
+    while (s.status == -1 && n < chunk) {
+        // loop condition of harmonic_path_cpu.cpp:185-187, evaluated on the current point
+        const uint32_t xc = f2u_x86(__fadd_rn(s.x, 0.5f)), yc = f2u_x86(__fadd_rn(s.y, 0.5f));
+        bool stop = (xc >= f.m1 || yc >= f.m0) || cell_locked(f, xc, yc);
+        for (uint32_t h = 0; h < s.nhist && !stop; ++h) {
+            const double dx = (double)__fsub_rn(s.x, s.hx[h]), dy = (double)__fsub_rn(s.y, s.hy[h]);
+            const float dist = __double2float_rn(__dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy))));
+            stop = dist < half_step;
+        }
+        if (!stop && (uint64_t)s.points * 2ull >= max_floats) {
+            stop = true;
+        }
+        if (stop) {
+            s.status = (s.points <= 2u) ? kPathInvalidPath : kPathOk;
+            break;
+        }
+        float gx, gy;
+        if (gradient_2d(f, s.x, s.y, cd, &gx, &gy) != kPathOk) {
+            s.status = kPathInvalidGradient;
+            break;
+        }
+        for (int h = 4; h > 0; --h) {
+            s.hx[h] = s.hx[h - 1];
+            s.hy[h] = s.hy[h - 1];
+        }
+        s.hx[0] = s.x;
+        s.hy[0] = s.y;
+        if (s.nhist < 5u) {
+            s.nhist++;
+        }
+        s.x = __fadd_rn(s.x, __fmul_rn(gx, step));
+        s.y = __fadd_rn(s.y, __fmul_rn(gy, step));
+        o[2 * n] = s.x;
+        o[2 * n + 1] = s.y;
+        n++;
+        s.points++;
+    }
+    states[i] = s;
+    emitted[i] = n;
+}
+
+__global__ void potential_gradient_kernel(FieldView2D f, float x, float y, float cd, int want_gradient,
+                                          float *out, int *ret)
+{
+    if (want_gradient) {
+        *ret = gradient_2d(f, x, y, cd, out, out + 1);
+    } else {
+        *ret = potential_2d(f, x, y, out);
+    }
+}
+
+}  // namespace epic_b200

@@ -1,0 +1,285 @@
+// sweep2d.cuh -- temporally blocked red-black log-sum-exp sweep, 2-D (4 neighbours).
+//
+// Replaces the reference kernels harmonic_update_2d_gpu / harmonic_update_and_check_2d_gpu /
+// harmonic_compute_max_delta_gpu (libepic/src/harmonic/harmonic_gpu.cu:39-153) with one kernel
+// that follows the *CPU* path's semantics (harmonic_cpu.cpp:38-78): colour phase "iteration `it`
+// updates interior cells with (it + x0 + x1) odd", locked cells skipped, delta = max |u_prev -
+// u_new| over the cells of the check sweep's colour.
+//
+// One CTA owns one tile: TH x 256 cells of shared memory, filled by a single TMA box load
+// (cp.async.bulk.tensor.2d, out-of-range cells zero-filled, so edge tiles need no branches).
+// It then performs up to T half-sweeps in place in shared memory.  Each half-sweep of a
+// red-black ordering only reads the other colour, so a sweep is race-free within the tile; data
+// that would have come from neighbouring tiles goes stale one ring per sweep, which is why the
+// tile carries a halo of T rows / HC = 4*ceil(T/4) columns and only the inner (TH-2T) x (256-2HC)
+// cells are written back (overlapped tiling).  Rows further than the remaining sweep count from
+// the output region are skipped (trapezoid), so the redundant work is ~T/2 rows per side.
+//
+// Thread mapping: a warp owns a panel of 128 columns (one float4 per lane) and marches down a
+// band of rows keeping rows r-1, r, r+1 in registers: per row and lane one LDS.128, one SHFL
+// (the one horizontal neighbour that lives in the adjacent lane), two updates, one STS.128.
+// The per-cell "may update" bits live in shared memory as one nibble per float4 group.
+#pragma once
+
+#include <cuda.h>
+#include <stdint.h>
+
+#include "math_policies.cuh"
+
+namespace epic_b200 {
+
+constexpr int kTileW = 256;            // columns of the shared-memory tile = one TMA box row
+constexpr int kGroups = kTileW / 4;    // float4 groups per tile row
+
+struct Sweep2DParams {
+    float *dst;                // destination ping-pong buffer (buffer-row 0)
+    const uint32_t *freemask;  // 1 bit per cell, buffer layout
+    const uint32_t *ctrl_done; // device flag: a previous check already converged -> no-op
+    uint32_t *delta_bits;      // atomicMax target for check sweeps
+    uint64_t pitch;            // floats per buffer row
+    uint32_t mask_wpr;         // mask words per buffer row
+    uint32_t m0, m1;           // global rows / columns of the grid
+    int32_t grow0;             // global row of buffer row 0 (negative for the first slab's ghost rows)
+    uint32_t buf_rows;         // rows present in the buffer
+    uint32_t own_lo, own_hi;   // buffer rows [own_lo, own_hi) are written by this slab
+    uint32_t TH, T, HC;        // tile rows, halo rows, halo columns
+    uint32_t out_h, out_w;     // TH - 2T, 256 - 2HC
+    uint32_t ntx;              // tiles per row of tiles
+    uint32_t count;            // half-sweeps in this pass (<= T)
+    uint32_t parity0;          // (it0 + grow0) & 1
+    uint32_t check;            // last sweep of the pass accumulates delta
+    uint32_t prefetch_stride;  // CTAs resident at once: tile (blockIdx + stride) is prefetched to L2
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, int x, int y, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
+        : "memory");
+}
+
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap *map, int x, int y)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(x), "r"(y)
+                 : "memory");
+}
+
+// Shared-memory carve-up (dynamic):
+//   [tile TH*256 floats][free nibbles TH*64 bytes][MathTables][mbarrier 8 B][warp maxima NT/32 floats]
+inline size_t sweep2d_smem_bytes(uint32_t TH, uint32_t NT)
+{
+    return (size_t)TH * kTileW * sizeof(float) + (size_t)TH * kGroups + sizeof(MathTables) + 8 + (NT / 32) * sizeof(float);
+}
+
+template <class Math, int NT>
+__global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1))
+sweep2d_kernel(const __grid_constant__ CUtensorMap src_map, const Sweep2DParams p, const Math math_in)
+{
+    if (*p.ctrl_done) {
+        return;  // a previous check sweep already met the termination rule
+    }
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *tile = reinterpret_cast<float *>(smem_raw);
+    uint8_t *lockt = smem_raw + (size_t)p.TH * kTileW * sizeof(float);
+    MathTables *tables = reinterpret_cast<MathTables *>(lockt + (size_t)p.TH * kGroups);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(tables + 1);
+    float *s_red = reinterpret_cast<float *>(bar + 1);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tx = blockIdx.x % p.ntx, ty = blockIdx.x / p.ntx;
+    const int gx0 = tx * (int)p.out_w - (int)p.HC;                 // grid column of tile column 0
+    const int by0 = (int)p.own_lo + ty * (int)p.out_h - (int)p.T;  // buffer row of tile row 0
+
+    if (tid == 0) {
+        mbar_init(bar, 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(bar, p.TH * kTileW * (uint32_t)sizeof(float));
+        tma_load_2d(tile, &src_map, gx0, by0, bar);
+        // Warm L2 with the tile the CTA that follows this one on the SM will ask for.
+        const uint32_t nb = blockIdx.x + p.prefetch_stride;
+        if (nb < gridDim.x) {
+            tma_prefetch_2d(&src_map, (int)(nb % p.ntx) * (int)p.out_w - (int)p.HC,
+                            (int)p.own_lo + (int)(nb / p.ntx) * (int)p.out_h - (int)p.T);
+        }
+    }
+
+    // While the TMA is in flight: libm tables and the tile's may-update nibbles.
+    load_math_tables(tables, tid, NT);
+    {
+        const int w0 = gx0 >> 5;        // floor division, gx0 may be negative
+        const int sh = gx0 - (w0 << 5); // 0, 4, ..., 28
+        for (int item = tid; item < (int)p.TH * 8; item += NT) {
+            const int r = item >> 3, j = item & 7;
+            const int b = by0 + r;
+            const int g = p.grow0 + b;              // global row
+            uint32_t bits = 0;
+            if (b >= 0 && b < (int)p.buf_rows && r > 0 && r < (int)p.TH - 1 && g > 0 && g < (int)p.m0 - 1) {
+                const uint32_t *row = p.freemask + (size_t)b * p.mask_wpr;
+                const int wa = w0 + j, wb = wa + 1;
+                const uint32_t a = (wa >= 0 && wa < (int)p.mask_wpr) ? __ldg(row + wa) : 0u;
+                const uint32_t c = (wb >= 0 && wb < (int)p.mask_wpr) ? __ldg(row + wb) : 0u;
+                bits = __funnelshift_r(a, c, sh);
+                if (j == 0) bits &= ~1u;            // tile column 0: no left neighbour in the tile
+                if (j == 7) bits &= ~0x80000000u;   // tile column 255
+                // the global border columns 0 and m1-1 are never updated (harmonic_cpu.cpp:46-51)
+                const int x_first = gx0 + j * 32;   // grid column of bit 0
+                if (x_first <= 0 && x_first + 31 >= 0) bits &= ~(1u << (0 - x_first));
+                const int x_last = (int)p.m1 - 1;
+                if (x_first <= x_last && x_first + 31 >= x_last) bits &= ~(1u << (x_last - x_first));
+            }
+            uint2 packed;
+            packed.x = (bits & 0xFu) | ((bits & 0xF0u) << 4) | ((bits & 0xF00u) << 8) | ((bits & 0xF000u) << 12);
+            bits >>= 16;
+            packed.y = (bits & 0xFu) | ((bits & 0xF0u) << 4) | ((bits & 0xF00u) << 8) | ((bits & 0xF000u) << 12);
+            *reinterpret_cast<uint2 *>(lockt + r * kGroups + j * 8) = packed;
+        }
+    }
+    mbar_wait(bar, 0);
+    __syncthreads();
+
+    Math math = math_in;
+    math.bind(tables);
+
+    const int panel = warp & 1;
+    const int band = warp >> 1;
+    constexpr int kBands = NT / 64;
+    const int col = panel * 128 + lane * 4;
+    const int grp = panel * 32 + lane;
+    const bool col_out = (col >= (int)p.HC) && (col < kTileW - (int)p.HC) && (gx0 + col < (int)p.m1);
+    float dmax = 0.0f;
+
+    for (uint32_t t = 0; t < p.count; ++t) {
+        // rows that still matter for the output region after the remaining sweeps
+        const int reach = (int)(p.count - 1 - t);
+        const int lo = (int)p.T - reach, hi = (int)p.TH - (int)p.T + reach;  // [lo, hi)
+        const int per = (hi - lo + kBands - 1) / kBands;
+        const int ra = lo + band * per;
+        const int rb = min(ra + per, hi);
+        const int pb = (int)((p.parity0 + t + (uint32_t)(by0 & 1) + (uint32_t)(gx0 & 1)) & 1u);
+        const bool checking = p.check && (t + 1 == p.count);
+
+        if (ra < rb) {
+            float4 up = *reinterpret_cast<const float4 *>(tile + (ra - 1) * kTileW + col);
+            float4 cur = *reinterpret_cast<const float4 *>(tile + ra * kTileW + col);
+            for (int r = ra; r < rb; ++r) {
+                const float4 dn = *reinterpret_cast<const float4 *>(tile + (r + 1) * kTileW + col);
+                const uint32_t nib = lockt[r * kGroups + grp];
+                // cell (r, c) is active when (it + x0 + x1) is odd  <=>  (pb + r + c) odd
+                const bool even_cols = ((r + pb) & 1) != 0;
+                const uint32_t active = even_cols ? (nib & 0x5u) : (nib & 0xAu);
+                float4 nw = cur;
+                if (__any_sync(0xffffffffu, active != 0)) {
+                    if (even_cols) {
+                        float left = __shfl_up_sync(0xffffffffu, cur.w, 1);
+                        if (lane == 0 && col > 0) {
+                            left = tile[r * kTileW + col - 1];
+                        }
+                        const float nx = math.update4(up.x, dn.x, left, cur.y);
+                        const float nz = math.update4(up.z, dn.z, cur.y, cur.w);
+                        if (active & 1u) nw.x = nx;
+                        if (active & 4u) nw.z = nz;
+                    } else {
+                        float right = __shfl_down_sync(0xffffffffu, cur.x, 1);
+                        if (lane == 31 && col + 4 < kTileW) {
+                            right = tile[r * kTileW + col + 4];
+                        }
+                        const float ny = math.update4(up.y, dn.y, cur.x, cur.z);
+                        const float nq = math.update4(up.w, dn.w, cur.z, right);
+                        if (active & 2u) nw.y = ny;
+                        if (active & 8u) nw.w = nq;
+                    }
+                    if (checking && col_out) {
+                        const int b = by0 + r;
+                        if (r >= (int)p.T && r < (int)p.TH - (int)p.T && b >= (int)p.own_lo && b < (int)p.own_hi) {
+                            // |prev - new| is 0 for cells that were not updated
+                            float d = fabsf(__fsub_rn(cur.x, nw.x));
+                            if (d > dmax) dmax = d;
+                            d = fabsf(__fsub_rn(cur.y, nw.y));
+                            if (d > dmax) dmax = d;
+                            d = fabsf(__fsub_rn(cur.z, nw.z));
+                            if (d > dmax) dmax = d;
+                            d = fabsf(__fsub_rn(cur.w, nw.w));
+                            if (d > dmax) dmax = d;
+                        }
+                    }
+                    *reinterpret_cast<float4 *>(tile + r * kTileW + col) = nw;
+                }
+                up = nw;
+                cur = dn;
+            }
+        }
+        __syncthreads();
+    }
+
+    // Write the output region (all of it, locked cells included: dst is a different buffer).
+    {
+        const int ogroups = (int)p.out_w / 4;
+        const int items = (int)p.out_h * ogroups;
+        for (int item = tid; item < items; item += NT) {
+            const int r = (int)p.T + item / ogroups;
+            const int c = (int)p.HC + (item % ogroups) * 4;
+            const int b = by0 + r;
+            const int gx = gx0 + c;
+            if (b >= (int)p.own_lo && b < (int)p.own_hi && gx < (int)p.pitch) {
+                const float4 v = *reinterpret_cast<const float4 *>(tile + r * kTileW + c);
+                *reinterpret_cast<float4 *>(p.dst + (size_t)b * p.pitch + gx) = v;
+            }
+        }
+    }
+
+    if (p.check) {
+        for (int o = 16; o > 0; o >>= 1) {
+            dmax = fmaxf(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+        }
+        if (lane == 0) {
+            s_red[warp] = dmax;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            float m = 0.0f;
+            for (int i = 0; i < NT / 32; ++i) {
+                m = fmaxf(m, s_red[i]);
+            }
+            if (m > 0.0f) {
+                atomicMax(p.delta_bits, __float_as_uint(m));
+            }
+        }
+    }
+}
+
+}  // namespace epic_b200

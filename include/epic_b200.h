@@ -1,0 +1,88 @@
+/*
+ * epic_b200.h -- slab-level C ABI of libepic.so (extension; the reference has no multi-GPU API).
+ *
+ * libepic's own ABI (epic/libepic.h) describes ONE grid held by ONE device.  To shard a grid over
+ * several B200s (one process per GPU) each rank holds a *slab*: the x0-range [row0, row0+rows) of
+ * the global grid plus `ghost` x0-layers on each side that mirror the neighbouring ranks' edge
+ * layers.  This header exposes the slab object that libepic's entry points are themselves built on
+ * (the reference functions it generalises: libepic/src/harmonic/harmonic_model_gpu.cu:34-204 for
+ * residency, harmonic_gpu.cu:327-434 for update / update_and_check / get_potential_values,
+ * harmonic_utilities_gpu.cu:66-138 for set_cells).  Halo exchange and the max-reduction of delta are
+ * the caller's (epic_b200/sharded.py does them with torch.distributed over NCCL); nothing in here
+ * talks to another device.
+ *
+ * Plain C: pointers and sizes only.  Return values are libepic's error codes (0 = success).
+ */
+#ifndef EPIC_B200_H
+#define EPIC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct epic_b200_field epic_b200_field;
+
+enum { EPIC_B200_MATH_STRICT = 0, EPIC_B200_MATH_FAST = 1, EPIC_B200_MATH_ENV = -1 };
+
+typedef struct epic_b200_info {
+    uint64_t pitch;          /* floats per innermost row in device memory */
+    uint64_t layer_floats;   /* floats per x0-layer in device memory */
+    uint64_t launches;       /* kernels launched by this field so far */
+    uint64_t device_bytes;   /* device memory held */
+    uint32_t sweeps_per_pass;/* T: half-sweeps fused into one kernel launch */
+    uint32_t tile_rows;      /* rows of the shared-memory tile (2-D) */
+    uint32_t math;           /* EPIC_B200_MATH_* in effect */
+    int32_t device;
+} epic_b200_info;
+
+/* n = 2 or 3; m[n] = GLOBAL dimensions; the slab owns x0 in [row0, row0+rows) and keeps `ghost`
+ * extra layers per side (0 for a whole grid).  math: EPIC_B200_MATH_*; device: ordinal or -1 for the
+ * current one; stream: a cudaStream_t to run on when use_stream != 0 (else a private stream). */
+int epic_b200_field_create(epic_b200_field **out, unsigned int n, const uint64_t *m, uint64_t row0, uint64_t rows,
+                           unsigned int ghost, int math, int device, void *stream, int use_stream);
+void epic_b200_field_destroy(epic_b200_field *f);
+int epic_b200_field_info(epic_b200_field *f, epic_b200_info *info);
+
+/* Dense host arrays covering `layers` x0-layers from global layer `first` (owned or ghost). */
+int epic_b200_field_upload_u(epic_b200_field *f, const float *host, uint64_t first, uint64_t layers);
+int epic_b200_field_upload_locked(epic_b200_field *f, const uint32_t *host, uint64_t first, uint64_t layers);
+int epic_b200_field_download_u(epic_b200_field *f, float *host, uint64_t first, uint64_t layers);
+int epic_b200_field_download_locked(epic_b200_field *f, uint32_t *host, uint64_t first, uint64_t layers);
+
+/* Enqueue `count` half-sweeps starting at iteration it0 (asynchronous).  With check_last the last
+ * sweep accumulates max|du| over the owned cells of its colour; read_delta fetches and resets it
+ * (synchronises the stream). */
+int epic_b200_field_run(epic_b200_field *f, uint32_t it0, uint32_t count, int check_last);
+int epic_b200_field_read_delta(epic_b200_field *f, float *delta);
+/* The complete reference loop on a whole-grid field (ghost == 0, rows == m[0]). */
+int epic_b200_field_solve(epic_b200_field *f, float epsilon, uint32_t stagger, uint32_t m_max, uint32_t *iterations,
+                          float *delta);
+int epic_b200_field_sync(epic_b200_field *f);
+
+/* Device address of global layer `layer` in the buffer that currently holds the field (it changes
+ * with every pass in 2-D: query after each run).  Null when the layer is not held by this slab. */
+void *epic_b200_field_layer_ptr(epic_b200_field *f, int64_t layer);
+
+int epic_b200_field_set_cells_2d(epic_b200_field *f, uint32_t k, const uint32_t *v, const uint32_t *types);
+int epic_b200_field_potential_2d(epic_b200_field *f, float x, float y, float *value);
+int epic_b200_field_gradient_2d(epic_b200_field *f, float x, float y, float cd, float *px, float *py);
+/* paths[i] is allocated with new float[2*k[i]]; release with epic_b200_free_path. */
+int epic_b200_field_paths_2d(epic_b200_field *f, uint32_t count, const float *starts, float step, float cd,
+                             uint32_t max_length, int *results, uint32_t *k, float **paths);
+void epic_b200_free_path(float *path);
+
+/* Self-test: the strict-math device functions (bit-exact twins of glibc expf / logf, see
+ * epic_b200/csrc/kernels/strict_math.h) against THIS host's libm, over every `stride`-th float of the
+ * argument ranges the sweep can produce (x <= 0 for expf, [1/8, 16) for logf). */
+int epic_b200_selftest_math(uint32_t stride, uint64_t *exp_checked, uint64_t *exp_mismatches, uint64_t *log_checked,
+                            uint64_t *log_mismatches);
+
+/* Library self-description: "epic_b200 <version> sm_100a". */
+const char *epic_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EPIC_B200_H */

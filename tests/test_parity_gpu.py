@@ -1,0 +1,248 @@
+"""Parity of the CUDA path, through the libepic C ABI, on a B200.
+
+Bit-exactness is the bar in the default (strict) math mode: fields, deltas and iteration counts are
+compared with golden vectors produced by the untouched reference CPU code (tests/golden/golden.json)
+and with the oracle on seeded inputs; paths are compared point for point.  The fast mode (MUFU
+ex2/lg2) is held to the stated tolerance |du| <= 1e-5*|u| + 1e-5 at equal iteration count.
+"""
+import ctypes as ct
+import os
+
+import numpy as np
+import pytest
+
+import common
+from epic_b200 import grids
+from epic_b200 import libepic as le
+from epic_b200.field import Field
+from epic_b200.harmonic import Harmonic
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+CASES_2D = ["box64", "random256", "random_ragged", "proc_maze", "basic", "umass", "maze"]
+CASES_3D = ["random48x3", "random3d_ragged"]
+
+
+def make_gpu(u, locked, eps, stagger):
+    return common.LibepicSolver(u, locked, eps, stagger, "gpu", paths_on="gpu")
+
+
+def make_gpu_host_paths(u, locked, eps, stagger):
+    return common.LibepicSolver(u, locked, eps, stagger, "gpu", paths_on="cpu")
+
+
+def test_strict_math_device_functions_equal_host_libm(libepic_built):
+    """Every float the sweep can feed to expf (x <= 0) and logf ([1/8, 16)): device result == host glibc."""
+    vals = [ct.c_uint64(0) for _ in range(4)]
+    assert libepic_built.epic_b200_selftest_math(1, *[ct.byref(v) for v in vals]) == 0
+    assert vals[0].value == 0xff800000 - 0x80000000 + 1 and vals[2].value == 0x41800000 - 0x3e000000
+    assert vals[1].value == 0, "%d expf mismatches" % vals[1].value
+    assert vals[3].value == 0, "%d logf mismatches" % vals[3].value
+
+
+@pytest.mark.parametrize("name", CASES_2D + CASES_3D)
+def test_checkpoints_bit_exact(golden, libepic_built, name):
+    """update / update_and_check call by call (the anytime node's usage): field and delta after k iterations."""
+    s = common.check_checkpoints(make_gpu, name, golden[name])
+    s.close()
+
+
+@pytest.mark.parametrize("name", CASES_2D + CASES_3D)
+def test_complete_gpu_bit_exact_and_paths(golden, libepic_built, name):
+    """harmonic_complete_gpu to epsilon: iterations, delta, every bit of the field; then the golden
+    paths extracted on the device-resident field (cell-for-cell and point-for-point)."""
+    s = common.check_complete(make_gpu, name, golden[name])
+    if s.h.n == 2:
+        common.check_paths(s, golden[name])
+        common.check_potentials(s, golden[name])
+    s.close()
+
+
+def test_plugin_sequence_host_paths(golden, libepic_built):
+    """nav_core plugin order (src/epic_nav_core_plugin.cpp:256-298): complete_gpu, then
+    harmonic_compute_path_2d_cpu on the host copy of u."""
+    s = common.check_complete(make_gpu_host_paths, "umass", golden["umass"])
+    common.check_paths(s, golden["umass"])
+
+
+def test_set_cells_sequence(golden, libepic_built):
+    s = common.check_set_cells(make_gpu, golden["set_cells"])
+    s.close()
+
+
+def test_set_cells_duplicates_last_edit_wins(libepic_built):
+    u, locked, eps, stagger = common.case_input("box64")
+    a = common.LibepicSolver(u.copy(), locked.copy(), eps, stagger, "gpu")
+    o = orc.Oracle(u.copy(), locked.copy(), eps, stagger)
+    v = np.array([[5, 5], [5, 5], [6, 6], [6, 6], [5, 5], [70, 3], [3, 70]], np.uint32)
+    t = np.array([0, 1, 1, 2, 2, 0, 0], np.uint32)
+    a.run_iterations(3)
+    o.run_iterations(3)
+    assert a.set_cells(v, t) == 0 and o.set_cells(v, t) == 0
+    a.run_iterations(50)
+    o.run_iterations(50)
+    assert np.array_equal(a.u, o.u)
+    a.close()
+
+
+def test_python_wrapper_double_initialise_sequence(golden, libepic_built):
+    """The reference's Harmonic.solve (python/epic/harmonic.py:73-97) initialises, calls complete_gpu
+    (which initialises again) and uninitialises: must work and leave null handles."""
+    u, locked, eps, stagger = common.case_input("box64")
+    h = Harmonic(u, locked, eps, stagger)
+    L = libepic_built
+    assert L.harmonic_initialize_dimension_size_gpu(ct.byref(h)) == 0
+    assert L.harmonic_initialize_potential_values_gpu(ct.byref(h)) == 0
+    assert L.harmonic_initialize_locked_gpu(ct.byref(h)) == 0
+    assert L.harmonic_complete_gpu(ct.byref(h), 1024) == 0
+    assert not h.d_m and not h.d_u and not h.d_locked and not h.d_delta
+    assert L.harmonic_uninitialize_dimension_size_gpu(ct.byref(h)) == 0
+    assert L.harmonic_uninitialize_potential_values_gpu(ct.byref(h)) == 0
+    assert L.harmonic_uninitialize_locked_gpu(ct.byref(h)) == 0
+    assert h.currentIteration == golden["box64"]["complete"]["iterations"]
+    assert common.sha1(h.field) == golden["box64"]["complete"]["sha1_u"]
+
+
+def test_execute_gpu_error_codes(libepic_built):
+    u, locked, eps, stagger = common.case_input("box64")
+    h = Harmonic(u, locked, eps, stagger)
+    h.initialize_gpu()
+    L = libepic_built
+    assert L.harmonic_execute_gpu(ct.byref(h), 100) == le.EPIC_ERROR_INVALID_CUDA_PARAM
+    h.epsilon = 0.0
+    assert L.harmonic_execute_gpu(ct.byref(h), 1024) == le.EPIC_ERROR_INVALID_DATA
+    h.epsilon = 1e-3
+    assert L.harmonic_initialize_gpu(ct.byref(h), 1024) == 0
+    assert L.harmonic_execute_gpu(ct.byref(h), 1024) == le.EPIC_ERROR_INVALID_DATA   # d_delta already set
+    assert L.harmonic_uninitialize_gpu(ct.byref(h)) == 0
+    assert L.harmonic_execute_gpu(ct.byref(h), 1024) == 0
+    h.uninitialize_gpu()
+
+
+def test_update_model_reuploads(libepic_built):
+    u, locked, eps, stagger = common.case_input("random_ragged")
+    s = common.LibepicSolver(u.copy(), locked.copy(), eps, stagger, "gpu")
+    o = orc.Oracle(u.copy(), locked.copy(), eps, stagger)
+    s.run_iterations(7)
+    # host-side edit + harmonic_update_model_gpu (reference harmonic_model_gpu.cu:172-204)
+    s.h.field[:] = u
+    s.h.locked_cells[40:60, 20:30] = 1
+    o.locked[40:60, 20:30] = 1
+    s.h.currentIteration = 0
+    s.h.update_model_gpu()
+    s.run_iterations(33)
+    o.run_iterations(33)
+    assert np.array_equal(s.u, o.u)
+    s.close()
+
+
+@pytest.mark.parametrize("shape,p,goals", [((700, 1100), 0.2, 5), ((1030, 517), 0.0, 1), ((300, 4099), 0.35, 9),
+                                           ((2048, 2048), 0.2, 16)])
+def test_seeded_grids_against_oracle(libepic_built, shape, p, goals):
+    """Shapes that straddle tile and pitch boundaries; fixed-K comparison with the oracle."""
+    u, locked = grids.random_obstacles(shape, p, goals, seed=77)
+    s = common.LibepicSolver(u.copy(), locked.copy(), 1e-3, 100, "gpu")
+    o = orc.Oracle(u.copy(), locked.copy(), 1e-3, 100, threads=8)
+    for k in (1, 2, 98, 1, 27):
+        s.run_iterations(k)
+        o.run_iterations(k)
+        assert s.iteration == o.iteration
+        assert np.array_equal(s.u, o.u), "field differs after %d iterations" % o.iteration
+        assert s.delta == o.delta
+    s.close()
+
+
+def test_seeded_3d_against_oracle(libepic_built):
+    u, locked = grids.random_obstacles((70, 45, 150), 0.2, 6, seed=5)
+    s = common.LibepicSolver(u.copy(), locked.copy(), 1e-3, 100, "gpu")
+    o = orc.Oracle(u.copy(), locked.copy(), 1e-3, 100, threads=8)
+    for k in (1, 2, 98, 1, 9):
+        s.run_iterations(k)
+        o.run_iterations(k)
+        assert np.array_equal(s.u, o.u) and s.delta == o.delta
+    s.close()
+
+
+def test_unlocked_border_is_never_updated(libepic_built):
+    """The reference sweeps interior cells only (harmonic_cpu.cpp:46-51), whatever `locked` says."""
+    u, locked = grids.random_obstacles((90, 300), 0.1, 3, seed=2)
+    locked[0, :] = locked[-1, :] = locked[:, 0] = locked[:, -1] = 0
+    s = common.LibepicSolver(u.copy(), locked.copy(), 1e-3, 100, "gpu")
+    o = orc.Oracle(u.copy(), locked.copy(), 1e-3, 100)
+    s.run_iterations(40)
+    o.run_iterations(40)
+    assert np.array_equal(s.u, o.u)
+    s.close()
+
+
+def test_fast_mode_within_stated_tolerance(libepic_built, golden):
+    """EPIC_MATH=fast (MUFU ex2/lg2): |u_gpu - u_cpu| <= 1e-5*|u_cpu| + 1e-5 at equal iteration count."""
+    u, locked, eps, stagger = common.case_input("random256")
+    f = Field(u.shape, math="fast")
+    f.upload(u, locked)
+    o = orc.Oracle(u.copy(), locked.copy(), eps, stagger)
+    f.run(0, 601, check_last=True)
+    d = f.read_delta()
+    o.run_iterations(601)
+    got = f.download_u()
+    free = locked == 0
+    err = np.abs(got[free] - o.u[free])
+    assert np.all(err <= 1e-5 * np.abs(o.u[free]) + 1e-5), "max err %g" % err.max()
+    assert np.array_equal(got[~free], o.u[~free])
+    assert abs(d - o.delta) <= 1e-5
+    f.close()
+
+
+def test_field_solve_matches_execute(libepic_built, golden):
+    u, locked, eps, stagger = common.case_input("proc_maze")
+    f = Field(u.shape)
+    f.upload(u, locked)
+    it, d = f.solve(eps, stagger)
+    g = golden["proc_maze"]["complete"]
+    assert it == g["iterations"] and common.hexf(d) == g["delta_hex"]
+    assert common.sha1(f.download_u()) == g["sha1_u"]
+    assert np.array_equal(f.download_locked(), locked)
+    f.close()
+
+
+def test_batched_paths_equal_single_paths(libepic_built, golden):
+    s = common.check_complete(make_gpu, "basic", golden["basic"])
+    s._resident_for_paths()
+    starts = grids.free_cells(s.h.locked_cells, 40, seed=3)
+    batch = s.h.compute_paths_gpu(starts, 0.05, 0.5, int(s.h.field.size / 0.05))
+    s.h.get_potential_values_gpu()
+    for (x, y), (ret, p) in zip(starts, batch):
+        r2, p2 = s.h.compute_path(float(x), float(y), 0.05, 0.5, int(s.h.field.size / 0.05), "cpu")
+        assert ret == r2 and np.array_equal(p, p2)
+    s.close()
+
+
+def test_round_trip_and_idempotence_at_full_size(libepic_built):
+    """16384^2 (BASELINE.json config 3) through size-independent properties: upload/download round trip,
+    locked cells never change, a sweep of one colour leaves the other colour untouched, and the delta of a
+    check sweep equals the max change observed from outside."""
+    shape = (16384, 16384)
+    u, locked = grids.random_obstacles(shape, 0.2, 64, seed=1234)
+    f = Field(shape)
+    f.upload(u, locked)
+    assert np.array_equal(f.download_u(first=8000, layers=64), u[8000:8064])
+    f.run(0, 1, check_last=True)
+    d = f.read_delta()
+    a = f.download_u()
+    changed = a != u
+    yy, xx = np.nonzero(changed)
+    assert np.all((yy + xx) % 2 == 1), "iteration 0 may only touch cells with (row + column) odd"
+    assert not changed[locked != 0].any()
+    assert d == np.abs(a[changed] - u[changed]).max()
+    f.run(1, 12, check_last=False)
+    b = f.download_u()
+    assert np.array_equal(b[locked != 0], u[locked != 0])
+    # rows 0..47 against the oracle on a band (the band's last rows lack their lower neighbours, so
+    # only rows that 13 sweeps cannot reach from the cut are compared)
+    band = 48 + 13
+    o = orc.Oracle(u[:band].copy(), np.where(np.arange(band)[:, None] == band - 1, 1, locked[:band]).astype(np.uint32),
+                   1e-3, 100, threads=8)
+    o.run_iterations(13)
+    assert np.array_equal(b[:48], o.u[:48])
+    f.close()
