@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric: Gcell-updates/s (and time-to-epsilon) of the log-space harmonic
+relaxation on the synthetic 16384 x 16384 random-obstacle grid (configs[2]), at 1/2/4/8 B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+  (N > 1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...)
+
+A "step" is one stagger period of the reference's solver loop over the whole grid: 100 red-black
+half-sweeps, the last one a convergence-check sweep (reference libepic/src/harmonic/harmonic_gpu.cu:266-290),
+i.e. 100 * (16384*16384/2) lattice-site updates.  One lattice-site update = one cell of the active colour in
+one half-sweep; algorithmic traffic 8 B per update.
+
+  value     device-resident throughput: grid already in HBM, K steps timed with CUDA events, max over ranks
+  e2e       the same steps through the reference-facing call path with HOST buffers inside the timed
+            region: harmonic_update_model_gpu (H2D of u and locked) -> harmonic_update_and_check_gpu +
+            99 x harmonic_update_gpu -> harmonic_get_potential_values_gpu (D2H of u)   [N = 1: libepic C ABI;
+            N > 1: the slab API, each rank moving its own slab]
+  roofline  HBM roofline of the sweep kernel: 8 B x updates / kernel time vs MEASURED_PEAKS.json
+  cpu_baseline  the reference's own CPU code (oracle/_ref, built from the untouched sources) on this host
+The grid (1 GiB of potentials per buffer) is 8x larger than L2, so nothing survives between passes.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SWEEPS_PER_STEP = 100
+ALGO_BYTES_PER_UPDATE = 8.0
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons sampled while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 7:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def workload(args):
+    return {"workload": "synthetic %dx%d random-obstacle grid (p=0.2, 64 goals, seed 1234), row-slab sharded"
+                        % (args.size, args.size),
+            "grid": [args.size, args.size], "epsilon": 1e-3, "stagger": SWEEPS_PER_STEP,
+            "sweeps_per_step": SWEEPS_PER_STEP, "updates_per_step": args.size * args.size // 2 * SWEEPS_PER_STEP,
+            "parallelism": "row-slab x%d" % args.gpus,
+            "l2": "grid (%.2f GiB per buffer) is larger than L2; no flush needed" % (args.size * args.size * 4 / 2**30)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU code on the host cores
+
+def cpu_reference_rate(size, rows, sweeps, warmup=0):
+    """(updates/s, description) of the reference CPU half-sweep over a `rows` x `size` band."""
+    from epic_b200 import grids
+    from oracle import oracle as orc
+    u, locked = grids.random_obstacles((size, size), 0.2, 64, seed=1234, row0=0, rows=rows)
+    locked[-1, :] = 1
+    if orc.have_ref():
+        solver, kind, cores = orc.Reference(u, locked, 1e-3, SWEEPS_PER_STEP), "reference", 1
+        what = "harmonic_update_cpu of the untouched reference sources (oracle/_ref), serial as shipped"
+    else:
+        cores = os.cpu_count() or 1
+        solver, kind = orc.Oracle(u, locked, 1e-3, SWEEPS_PER_STEP, threads=cores), "port"
+        what = "oracle port (oracle/harmonic_oracle.c), OpenMP over rows"
+    solver.iteration = 1
+    for _ in range(warmup):
+        solver.update()
+    t0 = time.perf_counter()
+    for _ in range(sweeps):
+        solver.update()
+    dt = time.perf_counter() - t0
+    updates = (rows - 2) * (size - 2) / 2.0 * sweeps
+    return updates / dt, dt, kind, cores, what
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # one step = one half-sweep over a band sized so that the whole run stays within ~150 s at ~25 M updates/s
+    budget_updates = 150.0 * 25e6 / max(1, args.steps + args.warmup)
+    rows = int(min(args.size, max(64, budget_updates / (args.size / 2.0))))
+    rate, dt, kind, cores, what = cpu_reference_rate(args.size, rows, args.steps, args.warmup)
+    value = rate / 1e9
+    sample = "%d half-sweeps (steps) over rows 0..%d of the %dx%d grid; %s" % (args.steps, rows - 1, args.size,
+                                                                             args.size, what)
+    line = {"impl": "reference", "metric": "Gcell-updates/s", "value": value, "unit": "Gcell-updates/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload(args), "gpu_launches": 0,
+            "cpu_baseline": {"value": value, "unit": "Gcell-updates/s", "cores": cores, "kind": kind, "sample": sample,
+                             "host_cores": os.cpu_count()},
+            "e2e": {"value": value, "unit": "Gcell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# native arm
+
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+
+    from epic_b200 import grids, libepic
+    from epic_b200.sharded import GpuSlab, ShardedSolver, partition
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d: launch with torch.distributed.run --nproc-per-node %d"
+                         % (args.gpus, world, args.gpus))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = libepic.load()
+    size = args.size
+    shape = (size, size)
+    updates_per_step = size * size // 2 * SWEEPS_PER_STEP
+
+    slab = GpuSlab(shape, rank, world, math=args.math)
+    lo, hi = slab.held_range()
+    u_held, locked_held = grids.random_obstacles(shape, 0.2, 64, seed=1234, row0=lo, rows=hi - lo)
+    # pinned host copies of what this rank holds: the e2e leg moves them inside the timed region
+    u_pin = torch.from_numpy(u_held).pin_memory()
+    l_pin = torch.from_numpy(locked_held.view(np.int32)).pin_memory()
+    u_host, l_host = u_pin.numpy(), l_pin.numpy().view(np.uint32)
+    slab.upload(u_host, l_host)
+    solver = ShardedSolver(slab)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident throughput ----
+    solver.run(1, True)                      # iteration 0 (a check sweep); steps then cover 1..100, 101..200, ...
+    for _ in range(args.warmup):
+        solver.run(SWEEPS_PER_STEP, True)
+    launches0 = slab.launches()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    with ClockSampler(local) as clocks:
+        start.record()
+        for _ in range(args.steps):
+            solver.run(SWEEPS_PER_STEP, True)
+        stop.record()
+        barrier()
+    ms = max_over_ranks(start.elapsed_time(stop))
+    launches = slab.launches() - launches0
+    value = updates_per_step * args.steps / (ms * 1e-3) / 1e9
+    delta_after = solver.delta
+    info = slab.field.info()
+
+    # ---- kernel-only timing for the roofline: the pass kernel alone, this rank's share ----
+    passes = 50
+    barrier()
+    start.record()
+    for i in range(passes):
+        slab.run_pass(solver.iteration + 4 * i, info["sweeps_per_pass"], False)
+    stop.record()
+    torch.cuda.synchronize()
+    kern_ms = start.elapsed_time(stop) / passes
+    own_updates_per_pass = slab.rows * size // 2 * info["sweeps_per_pass"]
+    achieved = own_updates_per_pass * ALGO_BYTES_PER_UPDATE / (kern_ms * 1e-3) / 1e9
+    peak, peak_src = peaks()
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(args.math)
+    # the throw-away passes above ran without halo exchange: restore a consistent state for the e2e leg
+    slab.upload(u_host, l_host)
+    solver.iteration = 0
+
+    # ---- end to end, host buffers in the timed region ----
+    e2e_steps = max(1, min(args.steps, 5))
+    if world == 1:
+        from epic_b200.harmonic import Harmonic
+        h = Harmonic(u_host, l_host, 1e-3, SWEEPS_PER_STEP)
+        h.initialize_gpu()
+        h2d = u_host.nbytes + l_host.nbytes
+        d2h = u_host.nbytes
+
+        def e2e_step():
+            h.currentIteration = 0
+            h.update_model_gpu()
+            h.run_iterations(SWEEPS_PER_STEP, "gpu")
+            h.get_potential_values_gpu()
+    else:
+        own = slice(slab.row0 - lo, slab.row0 - lo + slab.rows)
+        out_pin = torch.empty((slab.rows, size), dtype=torch.float32).pin_memory()
+        h2d = u_host.nbytes + l_host.nbytes
+        d2h = out_pin.numel() * 4
+
+        def e2e_step():
+            slab.upload(u_host, l_host)
+            solver.iteration = 0
+            solver.run(1, True)
+            solver.run(SWEEPS_PER_STEP - 1, False)
+            slab.field.download_u(first=slab.row0, layers=slab.rows, out=out_pin.numpy())
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    e2e_value = updates_per_step * e2e_steps / (e2e_ms * 1e-3) / 1e9
+    if world == 1:
+        h.uninitialize_gpu()
+
+    # ---- time to epsilon (reported beside the throughput; one run, not part of the timed steps) ----
+    tte = None
+    if args.tte:
+        slab.upload(u_host, l_host)
+        solver.iteration = 0
+        barrier()
+        t0 = time.perf_counter()
+        converged = False
+        while solver.iteration < args.tte_max_iterations:
+            solver.run((-solver.iteration) % SWEEPS_PER_STEP + 1, True)
+            if solver.delta < 1e-3 and solver.iteration >= size:
+                converged = True
+                break
+        barrier()
+        tte = {"seconds": max_over_ranks((time.perf_counter() - t0) * 1e3) / 1e3, "iterations": solver.iteration,
+               "delta": solver.delta, "epsilon": 1e-3, "converged": converged,
+               "note": "termination rule of harmonic_execute_gpu; excludes H2D/D2H"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        rate, dt, kind, cores, what = cpu_reference_rate(size, size, 4)
+        cpu = {"value": rate / 1e9, "unit": "Gcell-updates/s", "cores": cores, "kind": kind, "host_cores": os.cpu_count(),
+               "sample": "4 half-sweeps of the full %dx%d grid (%.1f s); %s" % (size, size, dt, what)}
+
+    if rank == 0:
+        line = {"metric": "Gcell-updates/s", "value": value, "unit": "Gcell-updates/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": dict(workload(args), math=args.math, sweeps_per_pass=info["sweeps_per_pass"],
+                               tile_rows=info["tile_rows"]),
+                "clocks": clocks.summary(),
+                "e2e": {"value": e2e_value, "unit": "Gcell-updates/s", "h2d_bytes_per_step": int(h2d) * world,
+                        "d2h_bytes_per_step": int(d2h) * world, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
+                        "path": "libepic C ABI (update_model -> update_and_check + 99 x update -> "
+                                "get_potential_values), pinned host arrays" if world == 1 else
+                                "slab API per rank (upload -> 100 sweeps with halo exchange -> download), pinned"},
+                "gpu_launches": int(launches),
+                "roofline": {"bound": "hbm", "achieved": achieved * world, "peak": peak * world, "unit": "GB/s",
+                             "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                             "kernel": "sweep2d_kernel<%s>" % ("StrictMath" if args.math == "strict" else "FastMath"),
+                             "kernel_ms": kern_ms, "algorithmic_bytes_per_update": ALGO_BYTES_PER_UPDATE,
+                             "updates_per_launch": own_updates_per_pass},
+                "cpu_baseline": cpu, "time_to_epsilon": tte, "delta_after_timed_steps": delta_after,
+                "library": lib.epic_b200_version().decode()}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["native", "reference"], default="native")
+    ap.add_argument("--size", type=int, default=16384)
+    ap.add_argument("--math", choices=["strict", "fast"], default=os.environ.get("EPIC_MATH", "strict"))
+    ap.add_argument("--tte", action="store_true", help="also run to epsilon once and report the time")
+    ap.add_argument("--tte-max-iterations", type=int, default=400000)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()
