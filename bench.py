@@ -162,6 +162,7 @@ def run_native(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
+    os.environ["EPIC_MATH"] = args.math      # the libepic C ABI takes its options from the environment
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = libepic.load()

@@ -1,0 +1,106 @@
+"""The sharded CUDA path.  On one GPU: several slabs of one grid live on the same device and exchange
+ghost layers by device copies -- this exercises everything slab-specific in the kernels (ghost offsets,
+colour parity of a slab that starts on an odd row, owned-row delta, first/last slab borders) and must be
+bit-identical to the reference golden vectors.  With >= 2 GPUs: the real thing over NCCL via torchrun."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import common
+from epic_b200 import grids
+from epic_b200.sharded import GpuSlab, ShardedSolver
+
+pytestmark = pytest.mark.gpu
+
+
+class LocalGroup:
+    """Drives `world` slabs that live in this process; halo exchange = device-to-device copies."""
+
+    def __init__(self, shape, world, math="strict"):
+        self.slabs = [GpuSlab(shape, r, world, math=math) for r in range(world)]
+        self.world = world
+        self.iteration = 0
+        self.delta = 0.0
+
+    def upload(self, u, locked):
+        for s in self.slabs:
+            lo, hi = s.held_range()
+            s.upload(u[lo:hi], locked[lo:hi])
+
+    def exchange(self):
+        g = self.slabs[0].ghost
+        for r in range(self.world - 1):
+            a, b = self.slabs[r], self.slabs[r + 1]
+            b.halo("recv_up", g).copy_(a.halo("send_down", g))
+            a.halo("recv_down", g).copy_(b.halo("send_up", g))
+
+    def run(self, count, check_last=False):
+        T = self.slabs[0].T
+        done = 0
+        while done < count:
+            c = min(T, count - done)
+            for s in self.slabs:
+                s.run_pass(self.iteration + done, c, check_last and done + c == count)
+            done += c
+            self.exchange()
+        self.iteration += count
+        if check_last:
+            self.delta = max(s.read_delta() for s in self.slabs)
+
+    def run_iterations(self, count, stagger):
+        left = count
+        while left > 0:
+            to_check = (-self.iteration) % stagger
+            if to_check < left:
+                self.run(to_check + 1, True)
+                left -= to_check + 1
+            else:
+                self.run(left, False)
+                left = 0
+
+    def field(self):
+        return np.concatenate([s.download_owned() for s in self.slabs], 0)
+
+
+@pytest.mark.parametrize("world,case", [(2, "random_ragged"), (3, "random256"), (5, "proc_maze"), (2, "random3d_ragged"),
+                                        (3, "random48x3")])
+def test_slabs_on_one_gpu_bit_identical(golden, libepic_built, world, case):
+    u, locked, eps, stagger = common.case_input(case)
+    grp = LocalGroup(u.shape, world)
+    grp.upload(u, locked)
+    done = 0
+    for k in sorted(int(c) for c in golden[case]["checkpoints"]):
+        grp.run_iterations(k - done, stagger)
+        done = k
+        g = golden[case]["checkpoints"][str(k)]
+        assert common.sha1(grp.field()) == g["sha1_u"], "%s x%d: field differs after %d iterations" % (case, world, k)
+        assert common.hexf(grp.delta) == g["delta_hex"]
+
+
+def test_world1_driver_on_gpu_solves_golden(golden, libepic_built):
+    u, locked, eps, stagger = common.case_input("basic")
+    slab = GpuSlab(u.shape, 0, 1)
+    slab.upload(u, locked)
+    s = ShardedSolver(slab)
+    it, delta = s.solve(eps, stagger)
+    g = golden["basic"]["complete"]
+    assert it == g["iterations"] and common.hexf(delta) == g["delta_hex"]
+    assert common.sha1(slab.download_owned()) == g["sha1_u"]
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_nccl_two_ranks_bit_identical(golden, libepic_built, tmp_path):
+    script = os.path.join(common.ROOT, "tests", "sharded_worker.py")
+    out = tmp_path / "out.json"
+    n = min(torch.cuda.device_count(), 4)
+    subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n),
+                    "--master-addr", "127.0.0.1", "--master-port", "29731", script, "proc_maze", str(out)],
+                   check=True, timeout=600)
+    res = json.load(open(out))
+    g = golden["proc_maze"]["complete"]
+    assert res["iterations"] == g["iterations"] and res["delta_hex"] == g["delta_hex"] and res["sha1_u"] == g["sha1_u"]
