@@ -25,8 +25,8 @@ __global__ void selftest_math_kernel(uint32_t first, uint32_t count, uint32_t st
     epic_b200::load_math_tables(&tables, threadIdx.x, blockDim.x);
     __syncthreads();
     epic_b200::StrictMath math;
+    math.init(epic_b200::kLog4);
     math.bind(&tables);
-    math.log2n = epic_b200::kLog4;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < count) {
         const float x = __uint_as_float(first + i * stride);
@@ -160,8 +160,9 @@ int epic_b200_selftest_math(uint32_t stride, uint64_t *exp_checked, uint64_t *ex
         return 4;
     }
     std::vector<float> host(chunk);
-    // which 0: every x <= 0 (bit patterns 0x80000000 .. 0xff800000); which 1: every normal x in [2^-3, 2^4)
-    const uint64_t lo[2] = {0x80000000ull, 0x3e000000ull}, hi[2] = {0xff800000ull + 1, 0x41800000ull};
+    // which 0: every x <= 0 (bit patterns 0x80000000 .. 0xff800000); which 1: every x in [1, 8] (the log
+    // argument is a sum of at most 6 terms, each <= 1 and one of them == 1)
+    const uint64_t lo[2] = {0x80000000ull, 0x3f800000ull}, hi[2] = {0xff800000ull + 1, 0x41000000ull + 1};
     uint64_t checked[2] = {0, 0}, bad[2] = {0, 0};
     int result = 0;
     for (int which = 0; which < 2 && result == 0; ++which) {

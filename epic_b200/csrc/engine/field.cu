@@ -97,6 +97,9 @@ FieldConfig config_from_env()
     if (const char *s = getenv("EPIC_TILE_ROWS")) {
         cfg.tile_rows = atoi(s);
     }
+    if (const char *s = getenv("EPIC_THREADS")) {
+        cfg.threads = atoi(s);
+    }
     if (const char *s = getenv("EPIC_DEVICE")) {
         cfg.device = atoi(s);
     }
@@ -177,6 +180,7 @@ int Field::create(Field **out, unsigned n, const uint64_t *gm, uint64_t row0, ui
             }
         }
         f->TH_ = pick;
+        f->NT_ = (cfg.threads == 256 || cfg.threads == 512) ? cfg.threads : ((pick >= 48) ? 512 : 256);
         if (cfg.tile_rows > 2 * f->T_ + 1 && cfg.tile_rows <= 200) {
             f->TH_ = cfg.tile_rows;
         }
@@ -459,14 +463,16 @@ int Field::launch_pass_2d(uint32_t it0, uint32_t count, bool check_last)
     p.count = count;
     p.parity0 = (uint32_t)(((int64_t)it0 + grow0_) & 1);
     p.check = check_last ? 1u : 0u;
-    const size_t smem = sweep2d_smem_bytes(p.TH, 256);
+    const size_t smem = sweep2d_smem_bytes(p.TH, (uint32_t)NT_);
     const uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(2, (227 * 1024) / (smem + 1024)));
     p.prefetch_stride = per_sm * (uint32_t)sms_;
     const uint32_t grid = p.ntx * nty;
 
     if (!attr_done_) {  // per device, so per field
         if (!allow_smem(sweep2d_kernel<StrictMath, 256>, 227 * 1024) ||
-            !allow_smem(sweep2d_kernel<FastMath, 256>, 227 * 1024)) {
+            !allow_smem(sweep2d_kernel<FastMath, 256>, 227 * 1024) ||
+            !allow_smem(sweep2d_kernel<StrictMath, 512>, 227 * 1024) ||
+            !allow_smem(sweep2d_kernel<FastMath, 512>, 227 * 1024)) {
             cudaGetLastError();
             return kInvalidCudaParam;
         }
@@ -474,13 +480,20 @@ int Field::launch_pass_2d(uint32_t it0, uint32_t count, bool check_last)
     }
     if (cfg_.math == MATH_STRICT) {
         StrictMath m;
-        m.t = nullptr;
-        m.log2n = kLog4;
-        sweep2d_kernel<StrictMath, 256><<<grid, 256, smem, stream_>>>(tmap_[cur_], p, m);
+        m.init(kLog4);
+        if (NT_ == 512) {
+            sweep2d_kernel<StrictMath, 512><<<grid, 512, smem, stream_>>>(tmap_[cur_], p, m);
+        } else {
+            sweep2d_kernel<StrictMath, 256><<<grid, 256, smem, stream_>>>(tmap_[cur_], p, m);
+        }
     } else {
         FastMath m;
         m.ln2n = 1.3862943611198906f;
-        sweep2d_kernel<FastMath, 256><<<grid, 256, smem, stream_>>>(tmap_[cur_], p, m);
+        if (NT_ == 512) {
+            sweep2d_kernel<FastMath, 512><<<grid, 512, smem, stream_>>>(tmap_[cur_], p, m);
+        } else {
+            sweep2d_kernel<FastMath, 256><<<grid, 256, smem, stream_>>>(tmap_[cur_], p, m);
+        }
     }
     launches_++;
     if (cudaGetLastError() != cudaSuccess) {
@@ -516,8 +529,7 @@ int Field::launch_pass_3d(uint32_t it0, uint32_t count, bool check_last)
         const uint32_t grid = (uint32_t)std::min<uint64_t>(work, (uint64_t)sms_ * 3);
         if (cfg_.math == MATH_STRICT) {
             StrictMath m;
-            m.t = nullptr;
-            m.log2n = kLog6;
+            m.init(kLog6);
             sweep3d_kernel<StrictMath><<<grid, 256, 0, stream_>>>(p, m);
         } else {
             FastMath m;

@@ -34,6 +34,7 @@ struct FieldConfig {
     MathMode math = MATH_STRICT;
     int sweeps_per_pass = 0;  // T; 0 = default
     int tile_rows = 0;        // 2-D: rows of the shared-memory tile (incl. halo); 0 = by grid size
+    int threads = 0;          // 2-D: threads per CTA (256 or 512); 0 = by tile size
     cudaStream_t stream = nullptr;  // run on this stream instead of a private one
     bool use_stream = false;
 };
@@ -133,7 +134,7 @@ private:
     size_t staging_bytes_ = 0;
 };
 
-// Parses EPIC_MATH (strict|fast), EPIC_SWEEPS_PER_PASS, EPIC_TILE_ROWS, EPIC_DEVICE.
+// Parses EPIC_MATH (strict|fast), EPIC_SWEEPS_PER_PASS, EPIC_TILE_ROWS, EPIC_THREADS, EPIC_DEVICE.
 FieldConfig config_from_env();
 
 }  // namespace epic_b200

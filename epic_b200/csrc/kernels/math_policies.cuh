@@ -24,8 +24,11 @@ struct MathTables {
     uint32_t exp_lo[32];
     uint32_t invc_hi[16];
     uint32_t invc_lo[16];
-    uint32_t logc_hi[16];
-    uint32_t logc_lo[16];
+    // y0[k*16 + i] = fma(k, Ln2, logc[i]) for k = 0..3: the log argument is a sum of 2n <= 6 terms in
+    // [1, 6], for which glibc's exponent k is 0..3, so its first FMA (and the int -> double conversion
+    // of k) becomes a lookup of the identical double.
+    uint32_t y0_hi[64];
+    uint32_t y0_lo[64];
 };
 
 static __device__ __constant__ uint64_t c_exp2f_table[32] = {EPIC_EXP2F_TABLE};
@@ -39,66 +42,76 @@ __device__ __forceinline__ void load_math_tables(MathTables *t, int tid, int nth
     }
     for (int i = tid; i < 16; i += nthreads) {
         const uint64_t a = (uint64_t)__double_as_longlong(c_logf_table[2 * i]);
-        const uint64_t b = (uint64_t)__double_as_longlong(c_logf_table[2 * i + 1]);
         t->invc_hi[i] = (uint32_t)(a >> 32);
         t->invc_lo[i] = (uint32_t)a;
-        t->logc_hi[i] = (uint32_t)(b >> 32);
-        t->logc_lo[i] = (uint32_t)b;
+    }
+    for (int i = tid; i < 64; i += nthreads) {
+        const double y0 = __fma_rn((double)(i >> 4), kLogLn2, c_logf_table[2 * (i & 15) + 1]);
+        const uint64_t b = (uint64_t)__double_as_longlong(y0);
+        t->y0_hi[i] = (uint32_t)(b >> 32);
+        t->y0_lo[i] = (uint32_t)b;
     }
 }
 
 struct StrictMath {
     const MathTables *t;
-    double log2n;  // glibc log(2.0 * n)
+    // Every double constant lives in the kernel-parameter (constant) bank, where DFMA/DADD read it as
+    // an operand; as literals they would be re-materialised with two moves per use.
+    double log2n;      // glibc log(2.0 * n)
+    double inv_ln2n;   // kExpInvLn2N
+    double shift;      // kExpShift
+    double c0, c1, c2; // kExpC0..2
+    double ln2, a0, a1, a2;
+
+    __host__ __device__ void init(double log_2n)
+    {
+        t = nullptr;
+        log2n = log_2n;
+        inv_ln2n = kExpInvLn2N;
+        shift = kExpShift;
+        c0 = kExpC0;
+        c1 = kExpC1;
+        c2 = kExpC2;
+        ln2 = kLogLn2;
+        a0 = kLogA0;
+        a1 = kLogA1;
+        a2 = kLogA2;
+    }
 
     __device__ __forceinline__ void bind(const MathTables *tables) { t = tables; }
 
+    // strict_expf_nonpos (strict_math.h), table split into 32-bit words.
     __device__ __forceinline__ float exp_nonpos(float x) const
     {
-        // strict_expf_nonpos with the table split into words (see strict_math.h for the algorithm)
-        if (x < -0x1.9fe368p6f) {
-            return 0.0f;
-        }
-        if (x < -0x1.9d1d9ep6f) {
-            return 0x1p-149f;
-        }
-        if (x != x) {
-            return x + x;
-        }
-        const double xd = (double)x;
-        const double kdp = __fma_rn(kExpInvLn2N, xd, kExpShift);
+        const double xd = (double)fmaxf(x, -104.5f);
+        const double kdp = __fma_rn(inv_ln2n, xd, shift);
         const uint32_t ki = (uint32_t)__double2loint(kdp);
-        const double kd = __dadd_rn(kdp, -kExpShift);
-        const double r = __fma_rn(kExpInvLn2N, xd, -kd);
+        const double kd = __dadd_rn(kdp, -shift);
+        const double r = __fma_rn(inv_ln2n, xd, -kd);
         const uint32_t idx = ki & 31u;
         const double s = __hiloint2double((int)(t->exp_hi[idx] + (ki << 15)), (int)t->exp_lo[idx]);
-        const double z = __fma_rn(kExpC0, r, kExpC1);
-        const double r2 = __dmul_rn(r, r);
-        double y = __fma_rn(kExpC2, r, 1.0);
-        y = __fma_rn(z, r2, y);
-        return __double2float_rn(__dmul_rn(y, s));
+        double y = __fma_rn(c0, r, c1);
+        y = __fma_rn(y, r, c2);
+        const double sr = __dmul_rn(s, r);
+        return __double2float_rn(__fma_rn(y, sr, s));
     }
 
+    // strict_logf_normal (strict_math.h) for x in [1, 2n], y0 from the (k, i) table.
     __device__ __forceinline__ float log_sum(float x) const
     {
         const uint32_t ix = __float_as_uint(x);
-        if (ix == 0x3f800000u) {
-            return 0.0f;
-        }
         const uint32_t tmp = ix - 0x3f330000u;
-        const uint32_t i = (tmp >> 19) & 15u;
-        const int k = (int)tmp >> 23;
+        const uint32_t ki = (tmp >> 19) & 63u;   // k * 16 + i, k <= 3
+        const uint32_t i = ki & 15u;
         const uint32_t iz = ix - (tmp & 0xff800000u);
         const double invc = __hiloint2double((int)t->invc_hi[i], (int)t->invc_lo[i]);
-        const double logc = __hiloint2double((int)t->logc_hi[i], (int)t->logc_lo[i]);
+        const double y0 = __hiloint2double((int)t->y0_hi[ki], (int)t->y0_lo[ki]);
         const double z = (double)__uint_as_float(iz);
         const double r = __fma_rn(z, invc, -1.0);
-        const double y0 = __fma_rn((double)k, kLogLn2, logc);
-        const double r2 = __dmul_rn(r, r);
-        double y = __fma_rn(kLogA1, r, kLogA2);
-        y = __fma_rn(kLogA0, r2, y);
-        y = __fma_rn(y, r2, __dadd_rn(y0, r));
-        return __double2float_rn(y);
+        double y = __fma_rn(a0, r, a1);
+        y = __fma_rn(y, r, a2);
+        y = __fma_rn(y, r, 1.0);
+        return __double2float_rn(__fma_rn(y, r, y0));
     }
 
     // std::max(a, b) of the reference: b only when a < b.
@@ -156,9 +169,10 @@ struct FastMath {
         asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
         return y;
     }
-    static __device__ __forceinline__ float e(float v, float mx)
+    // 2^((v - mx) * log2(e)) with the subtraction folded into one FFMA: mxl = -mx * log2(e)
+    static __device__ __forceinline__ float e(float v, float mxl)
     {
-        return ex2(__fmul_rn(__fsub_rn(v, mx), 1.4426950408889634f));
+        return ex2(__fmaf_rn(v, 1.4426950408889634f, mxl));
     }
     __device__ __forceinline__ float finish(float mx, float s) const
     {
@@ -167,14 +181,16 @@ struct FastMath {
     __device__ __forceinline__ float update4(float a, float b, float c, float d) const
     {
         const float mx = fmaxf(fmaxf(a, b), fmaxf(c, d));
-        const float s = __fadd_rn(__fadd_rn(e(a, mx), e(b, mx)), __fadd_rn(e(c, mx), e(d, mx)));
+        const float mxl = __fmul_rn(mx, -1.4426950408889634f);
+        const float s = __fadd_rn(__fadd_rn(e(a, mxl), e(b, mxl)), __fadd_rn(e(c, mxl), e(d, mxl)));
         return finish(mx, s);
     }
     __device__ __forceinline__ float update6(float a, float b, float c, float d, float g, float f) const
     {
         const float mx = fmaxf(fmaxf(fmaxf(a, b), fmaxf(c, d)), fmaxf(g, f));
-        const float s = __fadd_rn(__fadd_rn(__fadd_rn(e(a, mx), e(b, mx)), __fadd_rn(e(c, mx), e(d, mx))),
-                                  __fadd_rn(e(g, mx), e(f, mx)));
+        const float mxl = __fmul_rn(mx, -1.4426950408889634f);
+        const float s = __fadd_rn(__fadd_rn(__fadd_rn(e(a, mxl), e(b, mxl)), __fadd_rn(e(c, mxl), e(d, mxl))),
+                                  __fadd_rn(e(g, mxl), e(f, mxl)));
         return finish(mx, s);
     }
 };

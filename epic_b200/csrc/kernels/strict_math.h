@@ -134,44 +134,44 @@ EPIC_HD float strict_from_fbits(uint32_t b)
 #endif
 }
 
-// glibc expf for x <= 0 (or NaN).  `tab` = EPIC_EXP2F_TABLE (32 x uint64).
-// e_expf.c: the |x| >= 88 branch returns +0 below log(2^-150), the smallest denormal
-// (0x1.4p-75f squared, rounded) below log(2^-149) when WANT_ERRNO_UFLOW, and otherwise falls
-// through to the main path, whose final narrowing conversion produces the denormal results.
+// glibc expf for x <= 0.  `tab` = EPIC_EXP2F_TABLE (32 x uint64).
+//
+// e_expf.c returns +0 below log(2^-150) and the smallest denormal below log(2^-149) from its
+// |x| >= 88 branch; everywhere else it evaluates, in double,
+//     kd = round(x * N/ln2), r = x * N/ln2 - kd, s = 2^(kd/N) (table), y = (C0*r + C1)*r^2 + (C2*r + 1), y*s
+// and narrows to float.  What must be reproduced is the FLOAT result, and the argument domain is small
+// enough (2^31 floats) to check a cheaper evaluation exhaustively (tests/native/strict_math_check.cpp,
+// run by tests/test_strict_math.py on the CPU and epic_b200_selftest_math on the GPU):
+//   * clamping x at -104.5 replaces both underflow branches (the main path narrows to the same +0 /
+//     2^-149 results), and
+//   * the polynomial in Horner form with s folded in, s + (s*r) * ((C0*r + C1)*r + C2), needs 7 double
+//     operations instead of 8
+// give the same float as glibc for every x <= 0.  NaN is not reproduced bit for bit (payload).
 template <typename Table>
 EPIC_HD float strict_expf_nonpos(float x, const Table &tab)
 {
-    if (x < -0x1.9fe368p6f) {
-        return 0.0f;
-    }
-    if (x < -0x1.9d1d9ep6f) {
-        return 0x1p-149f;
-    }
-    if (x != x) {
-        return x + x;
-    }
-    const double xd = (double)x;
+    const float xc = (x < -104.5f) ? -104.5f : x;
+    const double xd = (double)xc;
     const double kdp = strict_fma(kExpInvLn2N, xd, kExpShift);   // z + SHIFT, contracted
     const uint64_t ki = strict_bits(kdp);
     const double kd = strict_add(kdp, -kExpShift);
     const double r = strict_fma(kExpInvLn2N, xd, -kd);           // z - kd, contracted
     const uint64_t t = tab[ki & 31] + (ki << 47);
     const double s = strict_from_bits(t);
-    const double z = strict_fma(kExpC0, r, kExpC1);
-    const double r2 = strict_mul(r, r);
-    double y = strict_fma(kExpC2, r, 1.0);
-    y = strict_fma(z, r2, y);
-    return (float)strict_mul(y, s);
+    double y = strict_fma(kExpC0, r, kExpC1);
+    y = strict_fma(y, r, kExpC2);
+    const double sr = strict_mul(s, r);
+    return (float)strict_fma(y, sr, s);
 }
 
 // glibc logf for normal x > 0.  `tab` = EPIC_LOGF_TABLE (16 x {invc, logc} doubles).
+// e_logf.c evaluates y0 = k*Ln2 + logc, r = z*invc - 1, (A1*r + A2 + A0*r^2)*r^2 + (y0 + r) in double;
+// the Horner form (((A0*r + A1)*r + A2)*r + 1)*r + y0 (one operation fewer) narrows to the same float
+// for every x in [1/8, 16), checked exhaustively like expf above.  (x == 1 gives +0 through this path.)
 template <typename Table>
 EPIC_HD float strict_logf_normal(float x, const Table &tab)
 {
     const uint32_t ix = strict_fbits(x);
-    if (ix == 0x3f800000u) {
-        return 0.0f;
-    }
     const uint32_t tmp = ix - 0x3f330000u;
     const uint32_t i = (tmp >> 19) & 15u;
     const int32_t k = (int32_t)tmp >> 23;
@@ -180,11 +180,10 @@ EPIC_HD float strict_logf_normal(float x, const Table &tab)
     const double z = (double)strict_from_fbits(iz);
     const double r = strict_fma(z, invc, -1.0);
     const double y0 = strict_fma((double)k, kLogLn2, logc);
-    const double r2 = strict_mul(r, r);
-    double y = strict_fma(kLogA1, r, kLogA2);
-    y = strict_fma(kLogA0, r2, y);
-    y = strict_fma(y, r2, strict_add(y0, r));
-    return (float)y;
+    double y = strict_fma(kLogA0, r, kLogA1);
+    y = strict_fma(y, r, kLogA2);
+    y = strict_fma(y, r, 1.0);
+    return (float)strict_fma(y, r, y0);
 }
 
 }  // namespace epic_b200

@@ -104,8 +104,67 @@ inline size_t sweep2d_smem_bytes(uint32_t TH, uint32_t NT)
     return (size_t)TH * kTileW * sizeof(float) + (size_t)TH * kGroups + sizeof(MathTables) + 8 + (NT / 32) * sizeof(float);
 }
 
+// One tile row for one lane: update the active colour of `cur` (in place) from the row above (`up`,
+// already holding this sweep's values of the other colour) and the row below (`dn`), store it.
+template <class Math>
+struct RowCtx {
+    const Math &math;
+    float *tile;
+    const uint8_t *lockt;
+    int col, grp, lane, by0;
+    bool checking;     // this sweep accumulates delta and this lane's columns are in the output region
+    int T, TH, own_lo, own_hi;
+    float dmax;
+
+    template <bool EVEN_COLS>
+    __device__ __forceinline__ void row(int r, const float4 &up, float4 &cur, const float4 &dn)
+    {
+        const uint32_t nib = lockt[r * kGroups + grp];
+        const uint32_t active = EVEN_COLS ? (nib & 0x5u) : (nib & 0xAu);
+        if (!__any_sync(0xffffffffu, active != 0)) {
+            return;
+        }
+        float4 nw = cur;
+        if (EVEN_COLS) {
+            float left = __shfl_up_sync(0xffffffffu, cur.w, 1);
+            if (lane == 0 && col > 0) {
+                left = tile[r * kTileW + col - 1];
+            }
+            const float nx = math.update4(up.x, dn.x, left, cur.y);
+            const float nz = math.update4(up.z, dn.z, cur.y, cur.w);
+            if (active & 1u) nw.x = nx;
+            if (active & 4u) nw.z = nz;
+        } else {
+            float right = __shfl_down_sync(0xffffffffu, cur.x, 1);
+            if (lane == 31 && col + 4 < kTileW) {
+                right = tile[r * kTileW + col + 4];
+            }
+            const float ny = math.update4(up.y, dn.y, cur.x, cur.z);
+            const float nq = math.update4(up.w, dn.w, cur.z, right);
+            if (active & 2u) nw.y = ny;
+            if (active & 8u) nw.w = nq;
+        }
+        if (checking) {
+            const int b = by0 + r;
+            if (r >= T && r < TH - T && b >= own_lo && b < own_hi) {
+                // |prev - new| is 0 for cells that were not updated
+                float d = fabsf(__fsub_rn(cur.x, nw.x));
+                if (d > dmax) dmax = d;
+                d = fabsf(__fsub_rn(cur.y, nw.y));
+                if (d > dmax) dmax = d;
+                d = fabsf(__fsub_rn(cur.z, nw.z));
+                if (d > dmax) dmax = d;
+                d = fabsf(__fsub_rn(cur.w, nw.w));
+                if (d > dmax) dmax = d;
+            }
+        }
+        *reinterpret_cast<float4 *>(tile + r * kTileW + col) = nw;
+        cur = nw;
+    }
+};
+
 template <class Math, int NT>
-__global__ void __launch_bounds__(NT, (NT <= 256 ? 2 : 1))
+__global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1))
 sweep2d_kernel(const __grid_constant__ CUtensorMap src_map, const Sweep2DParams p, const Math math_in)
 {
     if (*p.ctrl_done) {
@@ -194,54 +253,50 @@ sweep2d_kernel(const __grid_constant__ CUtensorMap src_map, const Sweep2DParams 
         const bool checking = p.check && (t + 1 == p.count);
 
         if (ra < rb) {
-            float4 up = *reinterpret_cast<const float4 *>(tile + (ra - 1) * kTileW + col);
-            float4 cur = *reinterpret_cast<const float4 *>(tile + ra * kTileW + col);
-            for (int r = ra; r < rb; ++r) {
-                const float4 dn = *reinterpret_cast<const float4 *>(tile + (r + 1) * kTileW + col);
-                const uint32_t nib = lockt[r * kGroups + grp];
-                // cell (r, c) is active when (it + x0 + x1) is odd  <=>  (pb + r + c) odd
-                const bool even_cols = ((r + pb) & 1) != 0;
-                const uint32_t active = even_cols ? (nib & 0x5u) : (nib & 0xAu);
-                float4 nw = cur;
-                if (__any_sync(0xffffffffu, active != 0)) {
-                    if (even_cols) {
-                        float left = __shfl_up_sync(0xffffffffu, cur.w, 1);
-                        if (lane == 0 && col > 0) {
-                            left = tile[r * kTileW + col - 1];
-                        }
-                        const float nx = math.update4(up.x, dn.x, left, cur.y);
-                        const float nz = math.update4(up.z, dn.z, cur.y, cur.w);
-                        if (active & 1u) nw.x = nx;
-                        if (active & 4u) nw.z = nz;
-                    } else {
-                        float right = __shfl_down_sync(0xffffffffu, cur.x, 1);
-                        if (lane == 31 && col + 4 < kTileW) {
-                            right = tile[r * kTileW + col + 4];
-                        }
-                        const float ny = math.update4(up.y, dn.y, cur.x, cur.z);
-                        const float nq = math.update4(up.w, dn.w, cur.z, right);
-                        if (active & 2u) nw.y = ny;
-                        if (active & 8u) nw.w = nq;
-                    }
-                    if (checking && col_out) {
-                        const int b = by0 + r;
-                        if (r >= (int)p.T && r < (int)p.TH - (int)p.T && b >= (int)p.own_lo && b < (int)p.own_hi) {
-                            // |prev - new| is 0 for cells that were not updated
-                            float d = fabsf(__fsub_rn(cur.x, nw.x));
-                            if (d > dmax) dmax = d;
-                            d = fabsf(__fsub_rn(cur.y, nw.y));
-                            if (d > dmax) dmax = d;
-                            d = fabsf(__fsub_rn(cur.z, nw.z));
-                            if (d > dmax) dmax = d;
-                            d = fabsf(__fsub_rn(cur.w, nw.w));
-                            if (d > dmax) dmax = d;
-                        }
-                    }
-                    *reinterpret_cast<float4 *>(tile + r * kTileW + col) = nw;
-                }
-                up = nw;
-                cur = dn;
+            RowCtx<Math> cx{math, tile, lockt, col, grp, lane, by0, checking && col_out, (int)p.T, (int)p.TH,
+                            (int)p.own_lo, (int)p.own_hi, dmax};
+            float4 a = *reinterpret_cast<const float4 *>(tile + (ra - 1) * kTileW + col);
+            float4 b = *reinterpret_cast<const float4 *>(tile + ra * kTileW + col);
+            float4 c;
+            int r = ra;
+            // cell (r, c) is active when (it + x0 + x1) is odd  <=>  (pb + r + c) odd; rows alternate
+            // between "even columns active" and "odd columns active", so the loop body is a pair of rows
+            // with the colour fixed at compile time.  a / b / c rotate roles (row above / row / row below)
+            // by renaming instead of by moves.
+            if (((r + pb) & 1) == 0) {  // first row updates the odd columns: peel it
+                c = *reinterpret_cast<const float4 *>(tile + (r + 1) * kTileW + col);
+                cx.template row<false>(r, a, b, c);
+                a = b;
+                b = c;
+                ++r;
             }
+            for (; r + 5 < rb; r += 6) {
+                c = *reinterpret_cast<const float4 *>(tile + (r + 1) * kTileW + col);
+                cx.template row<true>(r, a, b, c);
+                a = *reinterpret_cast<const float4 *>(tile + (r + 2) * kTileW + col);
+                cx.template row<false>(r + 1, b, c, a);
+                b = *reinterpret_cast<const float4 *>(tile + (r + 3) * kTileW + col);
+                cx.template row<true>(r + 2, c, a, b);
+                c = *reinterpret_cast<const float4 *>(tile + (r + 4) * kTileW + col);
+                cx.template row<false>(r + 3, a, b, c);
+                a = *reinterpret_cast<const float4 *>(tile + (r + 5) * kTileW + col);
+                cx.template row<true>(r + 4, b, c, a);
+                b = *reinterpret_cast<const float4 *>(tile + (r + 6) * kTileW + col);
+                cx.template row<false>(r + 5, c, a, b);
+            }
+            for (; r + 1 < rb; r += 2) {
+                c = *reinterpret_cast<const float4 *>(tile + (r + 1) * kTileW + col);
+                cx.template row<true>(r, a, b, c);
+                a = *reinterpret_cast<const float4 *>(tile + (r + 2) * kTileW + col);
+                cx.template row<false>(r + 1, b, c, a);
+                b = a;
+                a = c;
+            }
+            if (r < rb) {
+                c = *reinterpret_cast<const float4 *>(tile + (r + 1) * kTileW + col);
+                cx.template row<true>(r, a, b, c);
+            }
+            dmax = cx.dmax;
         }
         __syncthreads();
     }

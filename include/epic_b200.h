@@ -75,7 +75,7 @@ void epic_b200_free_path(float *path);
 
 /* Self-test: the strict-math device functions (bit-exact twins of glibc expf / logf, see
  * epic_b200/csrc/kernels/strict_math.h) against THIS host's libm, over every `stride`-th float of the
- * argument ranges the sweep can produce (x <= 0 for expf, [1/8, 16) for logf). */
+ * argument ranges the sweep can produce (x <= 0 for expf, [1, 8] for logf). */
 int epic_b200_selftest_math(uint32_t stride, uint64_t *exp_checked, uint64_t *exp_mismatches, uint64_t *log_checked,
                             uint64_t *log_mismatches);
 
