@@ -162,7 +162,6 @@ def run_native(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
-    os.environ["EPIC_MATH"] = args.math      # the libepic C ABI takes its options from the environment
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = libepic.load()
@@ -170,15 +169,17 @@ def run_native(args):
     shape = (size, size)
     updates_per_step = size * size // 2 * SWEEPS_PER_STEP
 
-    slab = GpuSlab(shape, rank, world, math=args.math)
-    lo, hi = slab.held_range()
+    # what this rank holds (owned rows + ghost rows), generated once and kept in pinned host memory: the
+    # e2e leg moves it inside the timed region
+    from epic_b200.sharded import partition as _partition
+    row0, nrows = _partition(size, world, rank)
+    ghost = 4 if world > 1 else 0
+    lo, hi = max(0, row0 - ghost), min(size, row0 + nrows + ghost)
     u_held, locked_held = grids.random_obstacles(shape, 0.2, 64, seed=1234, row0=lo, rows=hi - lo)
-    # pinned host copies of what this rank holds: the e2e leg moves them inside the timed region
     u_pin = torch.from_numpy(u_held).pin_memory()
     l_pin = torch.from_numpy(locked_held.view(np.int32)).pin_memory()
     u_host, l_host = u_pin.numpy(), l_pin.numpy().view(np.uint32)
-    slab.upload(u_host, l_host)
-    solver = ShardedSolver(slab)
+    del u_held, locked_held
 
     def barrier():
         torch.cuda.synchronize()
@@ -193,113 +194,115 @@ def run_native(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- device-resident throughput ----
-    solver.run(1, True)                      # iteration 0 (a check sweep); steps then cover 1..100, 101..200, ...
-    for _ in range(args.warmup):
-        solver.run(SWEEPS_PER_STEP, True)
-    launches0 = slab.launches()
-    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    with ClockSampler(local) as clocks:
-        start.record()
-        for _ in range(args.steps):
-            solver.run(SWEEPS_PER_STEP, True)
-        stop.record()
-        barrier()
-    ms = max_over_ranks(start.elapsed_time(stop))
-    launches = slab.launches() - launches0
-    value = updates_per_step * args.steps / (ms * 1e-3) / 1e9
-    delta_after = solver.delta
-    info = slab.field.info()
-
-    # ---- kernel-only timing for the roofline: the pass kernel alone, this rank's share ----
-    passes = 50
-    barrier()
-    start.record()
-    for i in range(passes):
-        slab.run_pass(solver.iteration + 4 * i, info["sweeps_per_pass"], False)
-    stop.record()
-    torch.cuda.synchronize()
-    kern_ms = start.elapsed_time(stop) / passes
-    own_updates_per_pass = slab.rows * size // 2 * info["sweeps_per_pass"]
-    achieved = own_updates_per_pass * ALGO_BYTES_PER_UPDATE / (kern_ms * 1e-3) / 1e9
     peak, peak_src = peaks()
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(tpath):
-        with open(tpath) as f:
-            traffic = json.load(f).get(args.math)
-    # the throw-away passes above ran without halo exchange: restore a consistent state for the e2e leg
-    slab.upload(u_host, l_host)
-    solver.iteration = 0
 
-    # ---- end to end, host buffers in the timed region ----
-    e2e_steps = max(1, min(args.steps, 5))
-    if world == 1:
-        from epic_b200.harmonic import Harmonic
-        h = Harmonic(u_host, l_host, 1e-3, SWEEPS_PER_STEP)
-        h.initialize_gpu()
-        h2d = u_host.nbytes + l_host.nbytes
-        d2h = u_host.nbytes
+    def measure(math, with_tte):
+        """All numbers of one arithmetic mode."""
+        os.environ["EPIC_MATH"] = math      # the libepic C ABI takes its options from the environment
+        slab = GpuSlab(shape, rank, world, math=math)
+        assert slab.held_range() == (lo, hi)
+        slab.upload(u_host, l_host)
+        solver = ShardedSolver(slab)
 
-        def e2e_step():
-            h.currentIteration = 0
-            h.update_model_gpu()
-            h.run_iterations(SWEEPS_PER_STEP, "gpu")
-            h.get_potential_values_gpu()
-    else:
-        own = slice(slab.row0 - lo, slab.row0 - lo + slab.rows)
-        out_pin = torch.empty((slab.rows, size), dtype=torch.float32).pin_memory()
-        h2d = u_host.nbytes + l_host.nbytes
-        d2h = out_pin.numel() * 4
+        # ---- device-resident throughput ----
+        with ClockSampler(local) as clocks:
+            solver.run(1, True)              # iteration 0 (a check sweep); steps then cover 1..100, 101..200, ...
+            for _ in range(args.warmup):
+                solver.run(SWEEPS_PER_STEP, True)
+            launches0 = slab.launches()
+            start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            start.record()
+            for _ in range(args.steps):
+                solver.run(SWEEPS_PER_STEP, True)
+            stop.record()
+            barrier()
+        ms = max_over_ranks(start.elapsed_time(stop))
+        launches = slab.launches() - launches0
+        value = updates_per_step * args.steps / (ms * 1e-3) / 1e9
+        delta_after = solver.delta
+        info = slab.field.info()
 
-        def e2e_step():
-            slab.upload(u_host, l_host)
-            solver.iteration = 0
-            solver.run(1, True)
-            solver.run(SWEEPS_PER_STEP - 1, False)
-            slab.field.download_u(first=slab.row0, layers=slab.rows, out=out_pin.numpy())
-    e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    barrier()
-    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
-    e2e_value = updates_per_step * e2e_steps / (e2e_ms * 1e-3) / 1e9
-    if world == 1:
-        h.uninitialize_gpu()
-
-    # ---- time to epsilon (reported beside the throughput; one run, not part of the timed steps) ----
-    tte = None
-    if args.tte:
+        # ---- kernel-only timing for the roofline: the pass kernel alone, this rank's share ----
+        passes = 50
+        barrier()
+        start.record()
+        for i in range(passes):
+            slab.run_pass(solver.iteration + info["sweeps_per_pass"] * i, info["sweeps_per_pass"], False)
+        stop.record()
+        torch.cuda.synchronize()
+        kern_ms = start.elapsed_time(stop) / passes
+        own_updates_per_pass = slab.rows * size // 2 * info["sweeps_per_pass"]
+        achieved = own_updates_per_pass * ALGO_BYTES_PER_UPDATE / (kern_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath) and size == 16384:
+            with open(tpath) as f:
+                traffic = json.load(f).get(math)
+                traffic = traffic / world if traffic else None
+        # the throw-away passes above ran without halo exchange: restore a consistent state
         slab.upload(u_host, l_host)
         solver.iteration = 0
+
+        # ---- end to end, host buffers in the timed region ----
+        e2e_steps = max(1, min(args.steps, 5))
+        if world == 1:
+            from epic_b200.harmonic import Harmonic
+            h = Harmonic(u_host, l_host, 1e-3, SWEEPS_PER_STEP)
+            h.initialize_gpu()
+            h2d = u_host.nbytes + l_host.nbytes
+            d2h = u_host.nbytes
+
+            def e2e_step():
+                h.currentIteration = 0
+                h.update_model_gpu()
+                h.run_iterations(SWEEPS_PER_STEP, "gpu")
+                h.get_potential_values_gpu()
+        else:
+            out_pin = torch.empty((slab.rows, size), dtype=torch.float32).pin_memory()
+            h2d = u_host.nbytes + l_host.nbytes
+            d2h = out_pin.numel() * 4
+
+            def e2e_step():
+                slab.upload(u_host, l_host)
+                solver.iteration = 0
+                solver.run(1, True)
+                solver.run(SWEEPS_PER_STEP - 1, False)
+                slab.field.download_u(first=slab.row0, layers=slab.rows, out=out_pin.numpy())
+        u_keep = u_host.copy() if world == 1 else None     # the C ABI downloads into the caller's u array
+        e2e_step()
         barrier()
         t0 = time.perf_counter()
-        converged = False
-        while solver.iteration < args.tte_max_iterations:
-            solver.run((-solver.iteration) % SWEEPS_PER_STEP + 1, True)
-            if solver.delta < 1e-3 and solver.iteration >= size:
-                converged = True
-                break
+        for _ in range(e2e_steps):
+            e2e_step()
         barrier()
-        tte = {"seconds": max_over_ranks((time.perf_counter() - t0) * 1e3) / 1e3, "iterations": solver.iteration,
-               "delta": solver.delta, "epsilon": 1e-3, "converged": converged,
-               "note": "termination rule of harmonic_execute_gpu; excludes H2D/D2H"}
+        e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        e2e_value = updates_per_step * e2e_steps / (e2e_ms * 1e-3) / 1e9
+        if world == 1:
+            h.uninitialize_gpu()
+            u_host[:] = u_keep
+            del u_keep
 
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        rate, dt, kind, cores, what = cpu_reference_rate(size, size, 4)
-        cpu = {"value": rate / 1e9, "unit": "Gcell-updates/s", "cores": cores, "kind": kind, "host_cores": os.cpu_count(),
-               "sample": "4 half-sweeps of the full %dx%d grid (%.1f s); %s" % (size, size, dt, what)}
-
-    if rank == 0:
-        line = {"metric": "Gcell-updates/s", "value": value, "unit": "Gcell-updates/s", "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": dict(workload(args), math=args.math, sweeps_per_pass=info["sweeps_per_pass"],
-                               tile_rows=info["tile_rows"]),
+        # ---- time to epsilon (reported beside the throughput; one run, not part of the timed steps) ----
+        tte = None
+        if with_tte:
+            slab.upload(u_host, l_host)
+            solver.iteration = 0
+            barrier()
+            t0 = time.perf_counter()
+            converged = False
+            while solver.iteration < args.tte_max_iterations:
+                solver.run((-solver.iteration) % SWEEPS_PER_STEP + 1, True)
+                if solver.delta < 1e-3 and solver.iteration >= size:
+                    converged = True
+                    break
+            barrier()
+            tte = {"seconds": max_over_ranks((time.perf_counter() - t0) * 1e3) / 1e3, "iterations": solver.iteration,
+                   "delta": solver.delta, "epsilon": 1e-3, "converged": converged,
+                   "note": "termination rule of harmonic_execute_gpu; excludes H2D/D2H"}
+        slab.field.close()
+        return {"value": value, "ms_per_step": ms / args.steps, "math": math,
+                "config_extra": {"math": math, "sweeps_per_pass": info["sweeps_per_pass"], "tile_rows": info["tile_rows"]},
                 "clocks": clocks.summary(),
                 "e2e": {"value": e2e_value, "unit": "Gcell-updates/s", "h2d_bytes_per_step": int(h2d) * world,
                         "d2h_bytes_per_step": int(d2h) * world, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
@@ -309,11 +312,36 @@ def run_native(args):
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "achieved": achieved * world, "peak": peak * world, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                             "kernel": "sweep2d_kernel<%s>" % ("StrictMath" if args.math == "strict" else "FastMath"),
+                             "kernel": "sweep2d_kernel<%s>" % ("StrictMath" if math == "strict" else "FastMath"),
                              "kernel_ms": kern_ms, "algorithmic_bytes_per_update": ALGO_BYTES_PER_UPDATE,
                              "updates_per_launch": own_updates_per_pass},
-                "cpu_baseline": cpu, "time_to_epsilon": tte, "delta_after_timed_steps": delta_after,
+                "time_to_epsilon": tte, "delta_after_timed_steps": delta_after}
+
+    main_res = measure(args.math, args.tte)
+    other = None
+    if not args.single_mode:
+        other = measure("fast" if args.math == "strict" else "strict", False)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        rate, dt, kind, cores, what = cpu_reference_rate(size, size, 4)
+        cpu = {"value": rate / 1e9, "unit": "Gcell-updates/s", "cores": cores, "kind": kind, "host_cores": os.cpu_count(),
+               "sample": "4 half-sweeps of the full %dx%d grid (%.1f s); %s" % (size, size, dt, what)}
+
+    if rank == 0:
+        line = {"metric": "Gcell-updates/s", "value": main_res["value"], "unit": "Gcell-updates/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": main_res["ms_per_step"],
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": dict(workload(args), **main_res["config_extra"]),
+                "clocks": main_res["clocks"], "e2e": main_res["e2e"], "gpu_launches": main_res["gpu_launches"],
+                "roofline": main_res["roofline"], "cpu_baseline": cpu, "time_to_epsilon": main_res["time_to_epsilon"],
+                "delta_after_timed_steps": main_res["delta_after_timed_steps"],
+                "modes": "strict = bit-identical to the reference CPU path (default of the library); fast = MUFU "
+                         "ex2/lg2, the arithmetic of the reference's own GPU kernel, |du| <= 1e-5*|u| + 1e-5",
                 "library": lib.epic_b200_version().decode()}
+        if other is not None:
+            line[other["math"] + "_mode"] = {k: other[k] for k in ("value", "ms_per_step", "e2e", "roofline", "clocks",
+                                                                   "gpu_launches")}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -330,6 +358,7 @@ def main():
     ap.add_argument("--tte", action="store_true", help="also run to epsilon once and report the time")
     ap.add_argument("--tte-max-iterations", type=int, default=400000)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--single-mode", action="store_true", help="measure only --math, not the other mode as well")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
     if args.impl == "reference":
