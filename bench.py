@@ -91,7 +91,7 @@ def workload(args):
                         % (args.size, args.size),
             "grid": [args.size, args.size], "epsilon": 1e-3, "stagger": SWEEPS_PER_STEP,
             "sweeps_per_step": SWEEPS_PER_STEP, "updates_per_step": args.size * args.size // 2 * SWEEPS_PER_STEP,
-            "parallelism": "row-slab x%d" % args.gpus,
+            "parallelism": "row-slab x%d" % args.gpus, "halo": (args.halo if args.gpus > 1 else None),
             "l2": "grid (%.2f GiB per buffer) is larger than L2; no flush needed" % (args.size * args.size * 4 / 2**30)}
 
 
@@ -199,7 +199,7 @@ def run_native(args):
     def measure(math, with_tte):
         """All numbers of one arithmetic mode."""
         os.environ["EPIC_MATH"] = math      # the libepic C ABI takes its options from the environment
-        slab = GpuSlab(shape, rank, world, math=math)
+        slab = GpuSlab(shape, rank, world, math=math, halo=args.halo)
         assert slab.held_range() == (lo, hi)
         slab.upload(u_host, l_host)
         solver = ShardedSolver(slab)
@@ -358,6 +358,7 @@ def main():
     ap.add_argument("--tte", action="store_true", help="also run to epsilon once and report the time")
     ap.add_argument("--tte-max-iterations", type=int, default=400000)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--halo", choices=["p2p", "nccl"], default="p2p", help="halo transport for --gpus > 1")
     ap.add_argument("--single-mode", action="store_true", help="measure only --math, not the other mode as well")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup

@@ -126,6 +126,27 @@ void *epic_b200_field_layer_ptr(epic_b200_field *f, int64_t layer)
 {
     return f ? (void *)f->impl->layer_ptr(layer) : nullptr;
 }
+int epic_b200_field_peer_export(epic_b200_field *f, void *blob, uint64_t blob_bytes)
+{
+    if (f == nullptr || blob == nullptr || blob_bytes < sizeof(epic_b200::PeerInfo)) {
+        return 2;
+    }
+    return f->impl->peer_export((epic_b200::PeerInfo *)blob);
+}
+int epic_b200_field_set_peer_ipc(epic_b200_field *f, int dir, const void *blob, uint64_t blob_bytes)
+{
+    if (f == nullptr || blob == nullptr || blob_bytes < sizeof(epic_b200::PeerInfo)) {
+        return 2;
+    }
+    return f->impl->set_peer_ipc(dir, (const epic_b200::PeerInfo *)blob);
+}
+int epic_b200_field_set_peer_local(epic_b200_field *f, int dir, epic_b200_field *other)
+{
+    if (f == nullptr || other == nullptr) {
+        return 2;
+    }
+    return f->impl->set_peer_local(dir, other->impl);
+}
 int epic_b200_field_set_cells_2d(epic_b200_field *f, uint32_t k, const uint32_t *v, const uint32_t *types)
 {
     return f ? f->impl->set_cells_2d(k, v, types) : 2;

@@ -52,6 +52,18 @@ EncodeTiledFn encode_tiled()
     return fn;
 }
 
+typedef CUresult (*StreamValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+
+StreamValue32Fn stream_memop(const char *name)
+{
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) {
+        return (StreamValue32Fn)p;
+    }
+    return nullptr;
+}
+
 struct DeviceGuard {
     int prev = -1;
     explicit DeviceGuard(int dev)
@@ -199,6 +211,7 @@ int Field::create(Field **out, unsigned n, const uint64_t *gm, uint64_t row0, ui
     }
     ok = ok && cudaMalloc(&f->freemask_, mbytes) == cudaSuccess && cudaMemset(f->freemask_, 0, mbytes) == cudaSuccess;
     ok = ok && cudaMalloc(&f->ctrl_, sizeof(Ctrl)) == cudaSuccess && cudaMemset(f->ctrl_, 0, sizeof(Ctrl)) == cudaSuccess;
+    ok = ok && cudaMalloc(&f->flags_, 256) == cudaSuccess && cudaMemset(f->flags_, 0, 256) == cudaSuccess;
     ok = ok && cudaMallocHost(&f->ctrl_host_, sizeof(Ctrl) * kSlots) == cudaSuccess;
     if (ok) {
         memset(f->ctrl_host_, 0, sizeof(Ctrl) * kSlots);
@@ -244,7 +257,9 @@ Field::~Field()
         for (int i = 0; i < 2; ++i) {
             if (u_[i]) cudaFree(u_[i]);
         }
+        close_peers();
         if (freemask_) cudaFree(freemask_);
+        if (flags_) cudaFree(flags_);
         if (ctrl_) cudaFree(ctrl_);
         if (ctrl_host_) cudaFreeHost(ctrl_host_);
         if (staging_) cudaFree(staging_);
@@ -294,6 +309,9 @@ int Field::upload_u(const float *host, uint64_t first, uint64_t layers)
         return kInvalidData;
     }
     DeviceGuard guard(cfg_.device);
+    if (wait_peers() != kSuccess) {   // neighbours may still be storing into the ghost layers
+        return kDeviceSynchronize;
+    }
     const uint64_t inner = gm_[n_ - 1];
     const uint64_t rows_per_layer = (n_ == 2) ? 1 : gm_[1];
     float *dst = u_[cur_] + (uint64_t)((int64_t)first - grow0_) * layer_floats_;
@@ -435,6 +453,144 @@ int Field::sync()
 }
 
 // ------------------------------------------------------------------------------------------------
+// Peer-to-peer halos
+
+int Field::peer_export(PeerInfo *out)
+{
+    if (out == nullptr) {
+        return kInvalidData;
+    }
+    DeviceGuard guard(cfg_.device);
+    memset(out, 0, sizeof(*out));
+    const int nbuf = (n_ == 2) ? 2 : 1;
+    for (int i = 0; i < nbuf; ++i) {
+        if (cudaIpcGetMemHandle(&out->u[i], u_[i]) != cudaSuccess) {
+            cudaGetLastError();
+            return kInvalidCudaParam;
+        }
+    }
+    if (cudaIpcGetMemHandle(&out->flags, flags_) != cudaSuccess) {
+        cudaGetLastError();
+        return kInvalidCudaParam;
+    }
+    out->own_lo = own_lo_;
+    out->own_hi = own_hi_;
+    out->layer_floats = layer_floats_;
+    out->buf_layers = buf_layers_;
+    out->ghost = ghost_;
+    out->device = cfg_.device;
+    return kSuccess;
+}
+
+int Field::set_peer_ipc(int dir, const PeerInfo *info)
+{
+    if (dir < 0 || dir > 1 || info == nullptr || info->layer_floats != layer_floats_ || ghost_ == 0 ||
+        info->ghost != ghost_) {
+        return kInvalidData;
+    }
+    DeviceGuard guard(cfg_.device);
+    if (stream_memop("cuStreamWaitValue32") == nullptr || stream_memop("cuStreamWriteValue32") == nullptr) {
+        return kInvalidCudaParam;
+    }
+    Peer &p = peer_[dir];
+    const int nbuf = (n_ == 2) ? 2 : 1;
+    bool ok = true;
+    for (int i = 0; i < nbuf && ok; ++i) {
+        ok = cudaIpcOpenMemHandle((void **)&p.u[i], info->u[i], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+    }
+    ok = ok && cudaIpcOpenMemHandle((void **)&p.flags, info->flags, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+    if (!ok) {
+        cudaGetLastError();
+        return kInvalidCudaParam;
+    }
+    p.own_lo = info->own_lo;
+    p.own_hi = info->own_hi;
+    p.ipc = true;
+    p.on = true;
+    return kSuccess;
+}
+
+int Field::set_peer_local(int dir, Field *other)
+{
+    if (dir < 0 || dir > 1 || other == nullptr || other->layer_floats_ != layer_floats_ || ghost_ == 0 ||
+        other->ghost_ != ghost_) {
+        return kInvalidData;
+    }
+    if (stream_memop("cuStreamWaitValue32") == nullptr || stream_memop("cuStreamWriteValue32") == nullptr) {
+        return kInvalidCudaParam;
+    }
+    if (other->cfg_.device != cfg_.device) {
+        DeviceGuard guard(cfg_.device);
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, cfg_.device, other->cfg_.device);
+        if (!can) {
+            return kInvalidCudaParam;
+        }
+        const cudaError_t e = cudaDeviceEnablePeerAccess(other->cfg_.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+            cudaGetLastError();
+            return kInvalidCudaParam;
+        }
+        cudaGetLastError();
+    }
+    Peer &p = peer_[dir];
+    p.u[0] = other->u_[0];
+    p.u[1] = other->u_[1];
+    p.flags = other->flags_;
+    p.own_lo = other->own_lo_;
+    p.own_hi = other->own_hi_;
+    p.ipc = false;
+    p.on = true;
+    return kSuccess;
+}
+
+void Field::close_peers()
+{
+    for (Peer &p : peer_) {
+        if (p.on && p.ipc) {
+            for (int i = 0; i < 2; ++i) {
+                if (p.u[i]) cudaIpcCloseMemHandle(p.u[i]);
+            }
+            if (p.flags) cudaIpcCloseMemHandle(p.flags);
+        }
+        p = Peer();
+    }
+}
+
+int Field::wait_peers()
+{
+    if (!has_peers()) {
+        return kSuccess;
+    }
+    static StreamValue32Fn wait_fn = stream_memop("cuStreamWaitValue32");
+    for (int d = 0; d < 2; ++d) {
+        if (peer_[d].on &&
+            wait_fn((CUstream)stream_, (CUdeviceptr)(flags_ + d), pass_count_, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS) {
+            return kDeviceSynchronize;
+        }
+    }
+    return kSuccess;
+}
+
+int Field::signal_peers()
+{
+    pass_count_++;
+    if (!has_peers()) {
+        return kSuccess;
+    }
+    static StreamValue32Fn write_fn = stream_memop("cuStreamWriteValue32");
+    for (int d = 0; d < 2; ++d) {
+        // the upper neighbour (d = 0) sees me as its lower one: its from_down word is flags[1]
+        if (peer_[d].on &&
+            write_fn((CUstream)stream_, (CUdeviceptr)(peer_[d].flags + (1 - d)), pass_count_, CU_STREAM_WRITE_VALUE_DEFAULT) !=
+                CUDA_SUCCESS) {
+            return kKernelExecution;
+        }
+    }
+    return kSuccess;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Sweeps
 
 int Field::launch_pass_2d(uint32_t it0, uint32_t count, bool check_last)
@@ -467,6 +623,16 @@ int Field::launch_pass_2d(uint32_t it0, uint32_t count, bool check_last)
     const uint32_t per_sm = (uint32_t)std::max<size_t>(1, std::min<size_t>(2, (227 * 1024) / (smem + 1024)));
     p.prefetch_stride = per_sm * (uint32_t)sms_;
     const uint32_t grid = p.ntx * nty;
+    p.halo_rows = (uint32_t)std::min<uint64_t>(ghost_, rows_);
+    if (peer_[0].on) {
+        p.peer_up = peer_[0].u[cur_ ^ 1] + peer_[0].own_hi * pitch_;
+    }
+    if (peer_[1].on) {
+        p.peer_down = peer_[1].u[cur_ ^ 1] + (peer_[1].own_lo - p.halo_rows) * pitch_;
+    }
+    if (wait_peers() != kSuccess) {
+        return kKernelExecution;
+    }
 
     if (!attr_done_) {  // per device, so per field
         if (!allow_smem(sweep2d_kernel<StrictMath, 256>, 227 * 1024) ||
@@ -500,7 +666,7 @@ int Field::launch_pass_2d(uint32_t it0, uint32_t count, bool check_last)
         return kKernelExecution;
     }
     cur_ ^= 1;
-    return kSuccess;
+    return signal_peers();
 }
 
 int Field::launch_pass_3d(uint32_t it0, uint32_t count, bool check_last)
@@ -525,6 +691,15 @@ int Field::launch_pass_3d(uint32_t it0, uint32_t count, bool check_last)
         p.row_blocks = (uint32_t)((gm_[1] + 7) / 8);
         p.it = it0 + s;
         p.check = (check_last && s + 1 == count) ? 1u : 0u;
+        if (peer_[0].on) {
+            p.peer_up = peer_[0].u[0] + peer_[0].own_hi * layer_floats_;
+        }
+        if (peer_[1].on) {
+            p.peer_down = peer_[1].u[0] + (peer_[1].own_lo - 1) * layer_floats_;
+        }
+        if (wait_peers() != kSuccess) {
+            return kKernelExecution;
+        }
         const uint64_t work = (uint64_t)rows_ * p.row_blocks * p.segs;
         const uint32_t grid = (uint32_t)std::min<uint64_t>(work, (uint64_t)sms_ * 3);
         if (cfg_.math == MATH_STRICT) {
@@ -538,6 +713,9 @@ int Field::launch_pass_3d(uint32_t it0, uint32_t count, bool check_last)
         }
         launches_++;
         if (cudaGetLastError() != cudaSuccess) {
+            return kKernelExecution;
+        }
+        if (signal_peers() != kSuccess) {
             return kKernelExecution;
         }
     }

@@ -39,6 +39,18 @@ struct FieldConfig {
     bool use_stream = false;
 };
 
+// What a neighbouring rank needs to store its edge layers straight into this slab's ghost layers and to
+// signal "pass p done": CUDA IPC handles of the two buffers and of the flag words, plus the geometry.
+struct PeerInfo {
+    cudaIpcMemHandle_t u[2];
+    cudaIpcMemHandle_t flags;
+    uint64_t own_lo, own_hi;     // buffer layers owned by that slab
+    uint64_t layer_floats;
+    uint64_t buf_layers;
+    uint32_t ghost;
+    int32_t device;
+};
+
 // Return codes are the reference's (libepic/include/epic/error_codes.h:31-46).
 class Field {
 public:
@@ -79,6 +91,16 @@ public:
     // Ghost-layer plumbing for sharded runs: device pointer into the CURRENT buffer at global
     // layer `layer` (owned or ghost).
     float *layer_ptr(int64_t layer);
+
+    // Peer-to-peer halos.  dir 0 = the slab above (lower x0), 1 = the slab below.  Once a peer is set,
+    // every pass (a) waits until that neighbour has signalled the completion of as many passes as this
+    // slab has issued, (b) stores its edge layers into the neighbour's ghost layers from inside the
+    // sweep kernel (NVLink peer stores), and (c) signals its own completion to the neighbour with a
+    // stream-ordered flag write.  All slabs of a grid must issue the same sequence of passes.
+    int peer_export(PeerInfo *out);
+    int set_peer_ipc(int dir, const PeerInfo *info);      // neighbour lives in another process
+    int set_peer_local(int dir, Field *other);            // neighbour lives in this process
+    bool has_peers() const { return peer_[0].on || peer_[1].on; }
 
     int sync();
     cudaStream_t stream() const { return stream_; }
@@ -132,6 +154,20 @@ private:
     size_t device_bytes_ = 0;
     void *staging_ = nullptr;    // device scratch for upload_locked / download_locked
     size_t staging_bytes_ = 0;
+
+    struct Peer {
+        bool on = false;
+        bool ipc = false;
+        float *u[2] = {nullptr, nullptr};  // the neighbour's two buffers, mapped here
+        uint32_t *flags = nullptr;         // the neighbour's flag words {from_up, from_down}
+        uint64_t own_lo = 0, own_hi = 0;
+    };
+    Peer peer_[2];
+    uint32_t *flags_ = nullptr;  // device: {from_up, from_down} = passes completed by the neighbours
+    uint32_t pass_count_ = 0;    // passes issued by this slab
+    int wait_peers();            // enqueue: flags_[d] >= pass_count_ for every peer
+    int signal_peers();          // enqueue: neighbour flags <- pass_count_
+    void close_peers();
 };
 
 // Parses EPIC_MATH (strict|fast), EPIC_SWEEPS_PER_PASS, EPIC_TILE_ROWS, EPIC_THREADS, EPIC_DEVICE.

@@ -49,6 +49,11 @@ struct Sweep2DParams {
     uint32_t parity0;          // (it0 + grow0) & 1
     uint32_t check;            // last sweep of the pass accumulates delta
     uint32_t prefetch_stride;  // CTAs resident at once: tile (blockIdx + stride) is prefetched to L2
+    // Sharded runs with peer-to-peer halos: the first / last `halo_rows` owned rows are ALSO stored into
+    // the neighbouring GPU's ghost rows (NVLink peer stores fused into this kernel's write-back).
+    float *peer_up;            // row 0 of the upper neighbour's ghost-below region in ITS destination buffer
+    float *peer_down;          // row 0 of the lower neighbour's ghost-above region
+    uint32_t halo_rows;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
@@ -313,6 +318,12 @@ sweep2d_kernel(const __grid_constant__ CUtensorMap src_map, const Sweep2DParams 
             if (b >= (int)p.own_lo && b < (int)p.own_hi && gx < (int)p.pitch) {
                 const float4 v = *reinterpret_cast<const float4 *>(tile + r * kTileW + c);
                 *reinterpret_cast<float4 *>(p.dst + (size_t)b * p.pitch + gx) = v;
+                if (p.peer_up != nullptr && b < (int)(p.own_lo + p.halo_rows)) {
+                    *reinterpret_cast<float4 *>(p.peer_up + (size_t)(b - (int)p.own_lo) * p.pitch + gx) = v;
+                }
+                if (p.peer_down != nullptr && b >= (int)(p.own_hi - p.halo_rows)) {
+                    *reinterpret_cast<float4 *>(p.peer_down + (size_t)(b - (int)(p.own_hi - p.halo_rows)) * p.pitch + gx) = v;
+                }
             }
         }
     }

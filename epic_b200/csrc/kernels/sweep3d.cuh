@@ -35,6 +35,10 @@ struct Sweep3DParams {
     uint32_t row_blocks;       // ceil(m1 / 8)
     uint32_t it;               // iteration (colour)
     uint32_t check;
+    // peer-to-peer halos (sharded runs): new values of the first / last owned layer are also stored
+    // into the neighbouring GPU's ghost layer
+    float *peer_up;            // the upper neighbour's ghost-below layer
+    float *peer_down;          // the lower neighbour's ghost-above layer
 };
 
 template <class Math>
@@ -129,6 +133,25 @@ sweep3d_kernel(const Sweep3DParams p, const Math math_in)
             if (active & 2u) c[1] = nw.y;
             if (active & 4u) c[2] = nw.z;
             if (active & 8u) c[3] = nw.w;
+            float *q = nullptr;
+            if (p.peer_up != nullptr && b0 == p.own_lo) {
+                q = p.peer_up + (uint64_t)x1 * p.pitch + x2;
+            } else if (p.peer_down != nullptr && b0 + 1 == p.own_hi) {
+                q = p.peer_down + (uint64_t)x1 * p.pitch + x2;
+            }
+            if (q != nullptr) {
+                if (active & 1u) q[0] = nw.x;
+                if (active & 2u) q[1] = nw.y;
+                if (active & 4u) q[2] = nw.z;
+                if (active & 8u) q[3] = nw.w;
+            }
+            if (p.peer_up != nullptr && p.peer_down != nullptr && b0 == p.own_lo && b0 + 1 == p.own_hi) {
+                q = p.peer_down + (uint64_t)x1 * p.pitch + x2;   // a one-layer slab feeds both neighbours
+                if (active & 1u) q[0] = nw.x;
+                if (active & 2u) q[1] = nw.y;
+                if (active & 4u) q[2] = nw.z;
+                if (active & 8u) q[3] = nw.w;
+            }
         }
     }
 

@@ -106,6 +106,21 @@ class Field:
     def layer_ptr(self, layer):
         return self._lib.epic_b200_field_layer_ptr(self._h, int(layer))
 
+    PEER_BLOB_BYTES = 256
+
+    def peer_export(self):
+        """Opaque bytes (CUDA IPC handles + geometry) a neighbouring rank needs for peer-to-peer halos."""
+        buf = ct.create_string_buffer(self.PEER_BLOB_BYTES)
+        self._check("peer_export", self._lib.epic_b200_field_peer_export(self._h, buf, self.PEER_BLOB_BYTES))
+        return buf.raw
+
+    def set_peer_ipc(self, direction, blob):
+        buf = ct.create_string_buffer(bytes(blob), self.PEER_BLOB_BYTES)
+        return self._lib.epic_b200_field_set_peer_ipc(self._h, int(direction), buf, self.PEER_BLOB_BYTES)
+
+    def set_peer_local(self, direction, other):
+        return self._lib.epic_b200_field_set_peer_local(self._h, int(direction), other._h)
+
     def set_cells(self, v, types):
         v = np.ascontiguousarray(v, dtype=np.uint32).reshape(-1)
         types = np.ascontiguousarray(types, dtype=np.uint32)

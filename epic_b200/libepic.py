@@ -127,6 +127,9 @@ EXTENSION_EXPORTS = {
     "epic_b200_field_set_cells_2d": (_F, ct.c_uint32, _P(ct.c_uint32), _P(ct.c_uint32)),
     "epic_b200_field_potential_2d": (_F, ct.c_float, ct.c_float, _P(ct.c_float)),
     "epic_b200_field_gradient_2d": (_F, ct.c_float, ct.c_float, ct.c_float, _P(ct.c_float), _P(ct.c_float)),
+    "epic_b200_field_peer_export": (_F, ct.c_void_p, ct.c_uint64),
+    "epic_b200_field_set_peer_ipc": (_F, ct.c_int, ct.c_void_p, ct.c_uint64),
+    "epic_b200_field_set_peer_local": (_F, ct.c_int, _F),
     "epic_b200_selftest_math": (ct.c_uint32, _P(ct.c_uint64), _P(ct.c_uint64), _P(ct.c_uint64), _P(ct.c_uint64)),
     "epic_b200_field_paths_2d": (_F, ct.c_uint32, _P(ct.c_float), ct.c_float, ct.c_float, ct.c_uint32, _P(ct.c_int),
                                  _P(ct.c_uint32), _P(_P(ct.c_float))),

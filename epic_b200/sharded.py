@@ -3,11 +3,16 @@
 The reference is single-device (no collectives anywhere); this is the multi-GPU
 step BASELINE.json's north_star adds.  Rank r owns the x0-layers [r*m0/W, (r+1)*m0/W) plus `ghost`
 layers on each side that mirror the neighbours' edge layers.  A pass (up to T half-sweeps fused in one
-kernel) needs ghost layers that were correct at its start, so after every pass each rank sends its
-first / last T owned layers to the rank above / below (NCCL send/recv over NVLink through
-torch.distributed; 2 messages of T*pitch floats per neighbour), and every check sweep is followed by
-ONE all-reduce(max) of the per-rank delta.  Red-black ordering makes the result independent of the
-partition: the sharded field is bit-identical to the single-GPU (and the CPU) field.
+kernel) needs ghost layers that were correct at its start, so after every pass each rank's first / last
+T owned layers must reach the rank above / below.  Two transports:
+  halo="p2p"   (default on one node) the sweep kernel itself stores those layers into the neighbours'
+               ghost layers over NVLink (CUDA IPC peer mappings) and passes are ordered between GPUs by
+               stream-ordered flag writes / waits: nothing on the host and no collective per pass;
+  halo="nccl"  NCCL send/recv through torch.distributed after every pass (2 messages of T*pitch floats
+               per neighbour).
+Every check sweep is followed by ONE all-reduce(max) of the per-rank delta.  Red-black ordering makes the
+result independent of the partition: the sharded field is bit-identical to the single-GPU (and the CPU)
+field.
 
 The driver is written against a small slab interface so that the same exchange schedule runs
   * on the product slab (epic_b200.field.Field, CUDA) -- GpuSlab below, and
@@ -31,7 +36,7 @@ class GpuSlab:
     """One rank's slab on its GPU, running on torch's current CUDA stream so that kernels and the
     NCCL transfers torch issues are ordered on the device without host synchronisation."""
 
-    def __init__(self, shape, rank, world, math="strict", device=None):
+    def __init__(self, shape, rank, world, math="strict", device=None, halo="p2p", group=None):
         self.shape = tuple(int(s) for s in shape)
         self.rank, self.world = rank, world
         self.row0, self.rows = partition(self.shape[0], world, rank)
@@ -46,6 +51,26 @@ class GpuSlab:
         assert world == 1 or self.T == self.ghost
         self.layer_floats = info["layer_floats"]
         self._views = {}
+        self.group = group
+        self.p2p = False
+        if world > 1 and halo == "p2p" and dist.is_initialized():
+            self._connect_peers()
+
+    def _connect_peers(self):
+        """Swap CUDA IPC handles with the neighbouring ranks; all ranks agree on the outcome."""
+        blobs = [None] * self.world
+        dist.all_gather_object(blobs, self.field.peer_export(), group=self.group)
+        ok = 1
+        if self.rank > 0 and self.field.set_peer_ipc(0, blobs[self.rank - 1]) != 0:
+            ok = 0
+        if self.rank < self.world - 1 and self.field.set_peer_ipc(1, blobs[self.rank + 1]) != 0:
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) != 1:
+            raise RuntimeError("peer-to-peer halo setup failed on some rank (CUDA IPC / peer access); "
+                               "construct GpuSlab(..., halo='nccl') to use NCCL send/recv instead")
+        self.p2p = True
 
     # global layers held (owned + ghost), clipped to the grid
     def held_range(self):
@@ -57,6 +82,10 @@ class GpuSlab:
         """u, locked: dense arrays covering held_range()."""
         lo, hi = self.held_range()
         self.field.upload(u, locked, first=lo, layers=hi - lo)
+        if self.p2p:
+            # a neighbour must not start storing into this slab's ghost layers before the upload is done
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)
 
     def download_owned(self):
         return self.field.download_u(first=self.row0, layers=self.rows)
@@ -105,8 +134,8 @@ class ShardedSolver:
 
     def exchange(self):
         """Refresh the ghost layers from the neighbours' freshly written edge layers."""
-        if self.world == 1:
-            return
+        if self.world == 1 or getattr(self.slab, "p2p", False):
+            return          # p2p: the sweep kernel has already stored the edge layers into the neighbours
         g = self.slab.ghost
         ops = []
         if self.rank > 0:
@@ -123,6 +152,10 @@ class ShardedSolver:
         """`count` half-sweeps from self.iteration; passes of T with a halo exchange after each."""
         T = self.slab.T
         done = 0
+        if self.world == 1 or getattr(self.slab, "p2p", False):
+            # nothing to do between passes on the host: let the library cut the range into passes
+            self.slab.run_pass(self.iteration, count, check_last)
+            done = count
         while done < count:
             c = min(T, count - done)
             self.slab.run_pass(self.iteration + done, c, check_last and done + c == count)

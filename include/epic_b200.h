@@ -65,6 +65,19 @@ int epic_b200_field_sync(epic_b200_field *f);
  * with every pass in 2-D: query after each run).  Null when the layer is not held by this slab. */
 void *epic_b200_field_layer_ptr(epic_b200_field *f, int64_t layer);
 
+/* Peer-to-peer halos over NVLink (one process per GPU on one node).  peer_export fills an opaque blob
+ * (EPIC_B200_PEER_BLOB_BYTES) holding CUDA IPC handles of this slab's buffers and flag words; the ranks
+ * exchange blobs (any transport) and hand the neighbours' blobs to set_peer_ipc: dir 0 = the slab above
+ * (lower x0), 1 = the slab below.  From then on every pass stores its edge layers straight into the
+ * neighbours' ghost layers from inside the sweep kernel and signals completion with a stream-ordered flag
+ * write; the next pass waits on the neighbours' flags.  No collective, no host involvement per pass.  All
+ * slabs must issue the same sequence of passes, and callers must synchronise all ranks after uploads.
+ * set_peer_local is the same for two slabs that live in one process. */
+#define EPIC_B200_PEER_BLOB_BYTES 256
+int epic_b200_field_peer_export(epic_b200_field *f, void *blob, uint64_t blob_bytes);
+int epic_b200_field_set_peer_ipc(epic_b200_field *f, int dir, const void *blob, uint64_t blob_bytes);
+int epic_b200_field_set_peer_local(epic_b200_field *f, int dir, epic_b200_field *other);
+
 int epic_b200_field_set_cells_2d(epic_b200_field *f, uint32_t k, const uint32_t *v, const uint32_t *types);
 int epic_b200_field_potential_2d(epic_b200_field *f, float x, float y, float *value);
 int epic_b200_field_gradient_2d(epic_b200_field *f, float x, float y, float cd, float *px, float *py);

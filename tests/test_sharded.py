@@ -51,7 +51,7 @@ class OracleSlab:
         return self.u[self.ghost:self.ghost + self.rows].copy()
 
     def run_pass(self, it0, count, check_last):
-        assert count <= self.T
+        assert count <= self.T or self.world == 1   # a lone slab has no ghost layers to go stale
         self.nlaunch += 1
         view_u = self.u[self.lo_off:self.hi_off]
         view_l = self.locked[self.lo_off:self.hi_off]

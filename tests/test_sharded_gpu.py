@@ -21,11 +21,16 @@ pytestmark = pytest.mark.gpu
 class LocalGroup:
     """Drives `world` slabs that live in this process; halo exchange = device-to-device copies."""
 
-    def __init__(self, shape, world, math="strict"):
+    def __init__(self, shape, world, math="strict", p2p=False):
         self.slabs = [GpuSlab(shape, r, world, math=math) for r in range(world)]
         self.world = world
         self.iteration = 0
         self.delta = 0.0
+        self.p2p = p2p
+        if p2p:     # the kernels store the edge layers into the neighbour slab themselves
+            for r in range(world - 1):
+                assert self.slabs[r].field.set_peer_local(1, self.slabs[r + 1].field) == 0
+                assert self.slabs[r + 1].field.set_peer_local(0, self.slabs[r].field) == 0
 
     def upload(self, u, locked):
         for s in self.slabs:
@@ -33,6 +38,8 @@ class LocalGroup:
             s.upload(u[lo:hi], locked[lo:hi])
 
     def exchange(self):
+        if self.p2p:
+            return
         g = self.slabs[0].ghost
         for r in range(self.world - 1):
             a, b = self.slabs[r], self.slabs[r + 1]
@@ -67,11 +74,12 @@ class LocalGroup:
         return np.concatenate([s.download_owned() for s in self.slabs], 0)
 
 
+@pytest.mark.parametrize("p2p", [False, True])
 @pytest.mark.parametrize("world,case", [(2, "random_ragged"), (3, "random256"), (5, "proc_maze"), (2, "random3d_ragged"),
                                         (3, "random48x3")])
-def test_slabs_on_one_gpu_bit_identical(golden, libepic_built, world, case):
+def test_slabs_on_one_gpu_bit_identical(golden, libepic_built, world, case, p2p):
     u, locked, eps, stagger = common.case_input(case)
-    grp = LocalGroup(u.shape, world)
+    grp = LocalGroup(u.shape, world, p2p=p2p)
     grp.upload(u, locked)
     done = 0
     for k in sorted(int(c) for c in golden[case]["checkpoints"]):
@@ -98,9 +106,12 @@ def test_nccl_two_ranks_bit_identical(golden, libepic_built, tmp_path):
     script = os.path.join(common.ROOT, "tests", "sharded_worker.py")
     out = tmp_path / "out.json"
     n = min(torch.cuda.device_count(), 4)
-    subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n),
-                    "--master-addr", "127.0.0.1", "--master-port", "29731", script, "proc_maze", str(out)],
-                   check=True, timeout=600)
-    res = json.load(open(out))
-    g = golden["proc_maze"]["complete"]
-    assert res["iterations"] == g["iterations"] and res["delta_hex"] == g["delta_hex"] and res["sha1_u"] == g["sha1_u"]
+    for halo, case in (("p2p", "proc_maze"), ("nccl", "proc_maze"), ("p2p", "random48x3")):
+        subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n),
+                        "--master-addr", "127.0.0.1", "--master-port", "29731", script, case, str(out), halo],
+                       check=True, timeout=600)
+        res = json.load(open(out))
+        g = golden[case]["complete"]
+        assert res["halo"] == halo
+        assert res["iterations"] == g["iterations"] and res["delta_hex"] == g["delta_hex"]
+        assert res["sha1_u"] == g["sha1_u"], "%s over %s differs from the reference" % (case, halo)
