@@ -337,7 +337,7 @@ def run_native(args):
                 "roofline": main_res["roofline"], "cpu_baseline": cpu, "time_to_epsilon": main_res["time_to_epsilon"],
                 "delta_after_timed_steps": main_res["delta_after_timed_steps"],
                 "modes": "strict = bit-identical to the reference CPU path (default of the library); fast = MUFU "
-                         "ex2/lg2, the arithmetic of the reference's own GPU kernel, |du| <= 1e-5*|u| + 1e-5",
+                         "ex2/lg2, the arithmetic of the reference's own GPU kernel, |du| <= 1e-5*|u| + 4e-7*iterations at matched epsilon",
                 "library": lib.epic_b200_version().decode()}
         if other is not None:
             line[other["math"] + "_mode"] = {k: other[k] for k in ("value", "ms_per_step", "e2e", "roofline", "clocks",

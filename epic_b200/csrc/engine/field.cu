@@ -2,6 +2,7 @@
 // multiply-add in the kernels is an explicit intrinsic).
 #include "field.h"
 
+#include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -176,25 +177,66 @@ int Field::create(Field **out, unsigned n, const uint64_t *gm, uint64_t row0, ui
         f->T_ = std::min(cfg.sweeps_per_pass, 8);
     }
     if (n == 2) {
+        // Tile geometry: estimate the time of one pass for every candidate (threads, tile rows) and keep
+        // the cheapest.  A tile costs its output rows over `eff`; an SM works through its tiles k at a time (k =
+        // resident CTAs); `eff` is the measured relative speed of the candidate on a grid large enough
+        // to hide wave effects (tools/sweep_timing.py, profiles/r01c_tile_candidates.md).  Small grids
+        // end up with small tiles (every SM gets work, short passes), slabs of a sharded grid with a
+        // tile height that fills the last wave.
+        if (!allow_smem(sweep2d_kernel<StrictMath, 256>, 227 * 1024) ||
+            !allow_smem(sweep2d_kernel<FastMath, 256>, 227 * 1024) ||
+            !allow_smem(sweep2d_kernel<StrictMath, 512>, 227 * 1024) ||
+            !allow_smem(sweep2d_kernel<FastMath, 512>, 227 * 1024)) {
+            cudaGetLastError();
+            delete f;
+            return kInvalidCudaParam;
+        }
+        f->attr_done_ = true;
+        struct Cand { int nt, th; float eff_strict, eff_fast; };
+        static const Cand cands[] = {{512, 96, 1.00f, 0.98f}, {512, 88, 0.99f, 0.96f}, {512, 80, 0.977f, 0.94f},
+                                     {512, 72, 0.96f, 0.97f}, {512, 64, 0.95f, 1.00f}, {256, 64, 0.915f, 0.985f},
+                                     {256, 56, 0.89f, 0.99f}, {256, 48, 0.874f, 0.997f}, {256, 40, 0.84f, 0.98f},
+                                     {256, 32, 0.805f, 0.97f}, {256, 24, 0.70f, 0.85f}, {256, 16, 0.50f, 0.60f}};
         const int HC = 4 * ((f->T_ + 3) / 4);
         const int out_w = kTileW - 2 * HC;
         const uint64_t ntx = (gm[1] + out_w - 1) / out_w;
-        const int cands[] = {96, 64, 48, 32, 24};
-        int pick = 0;
-        for (int th : cands) {
-            if (th <= 2 * f->T_ + 4) {
+        double best = 0.0;
+        for (const Cand &c : cands) {
+            if (c.th <= 2 * f->T_ + 4) {
                 continue;
             }
-            const uint64_t nty = (rows + (th - 2 * f->T_) - 1) / (th - 2 * f->T_);
-            pick = th;
-            if (ntx * nty >= (uint64_t)f->sms_) {
-                break;
+            const size_t smem = sweep2d_smem_bytes((uint32_t)c.th, (uint32_t)c.nt);
+            int k = 0;
+            cudaError_t e;
+            if (cfg.math == MATH_STRICT) {
+                e = (c.nt == 512) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k, sweep2d_kernel<StrictMath, 512>, 512, smem)
+                                  : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k, sweep2d_kernel<StrictMath, 256>, 256, smem);
+            } else {
+                e = (c.nt == 512) ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k, sweep2d_kernel<FastMath, 512>, 512, smem)
+                                  : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k, sweep2d_kernel<FastMath, 256>, 256, smem);
+            }
+            if (e != cudaSuccess || k < 1) {
+                cudaGetLastError();
+                k = 1;
+            }
+            const uint64_t nty = (rows + (c.th - 2 * f->T_) - 1) / (c.th - 2 * f->T_);
+            const double tiles = (double)(ntx * nty);
+            const double eff = (cfg.math == MATH_STRICT) ? c.eff_strict : c.eff_fast;
+            const double per_tile = (double)(c.th - 2 * f->T_) / eff;   // output rows per tile over relative speed
+            const double by_sm = ceil(tiles / f->sms_) * per_tile;                          // perfect packing
+            const double by_wave = ceil(tiles / ((double)f->sms_ * k)) * k * per_tile;      // whole waves
+            const double t = 0.5 * (by_sm + by_wave);
+            if (best == 0.0 || t < best) {
+                best = t;
+                f->TH_ = c.th;
+                f->NT_ = c.nt;
             }
         }
-        f->TH_ = pick;
-        f->NT_ = (cfg.threads == 256 || cfg.threads == 512) ? cfg.threads : ((pick >= 48) ? 512 : 256);
         if (cfg.tile_rows > 2 * f->T_ + 1 && cfg.tile_rows <= 200) {
             f->TH_ = cfg.tile_rows;
+        }
+        if (cfg.threads == 256 || cfg.threads == 512) {
+            f->NT_ = cfg.threads;
         }
     }
 

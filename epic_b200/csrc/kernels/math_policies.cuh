@@ -6,8 +6,8 @@
 //               :107-124), so the field is bit-identical to harmonic_complete_cpu's.
 //   FastMath    MUFU ex2/lg2 approximations, the arithmetic class of the reference's own GPU
 //               kernel (harmonic_gpu.cu:52-61: __expf, __logf, constant 1.38629436f).  Stated
-//               tolerance against the CPU path: |du| <= 1e-5*|u| + 1e-5 at equal iteration count
-//               (tests/test_parity_gpu.py).
+//               tolerance against the CPU path at matched epsilon: same iteration count and
+//               |du| <= 1e-5*|u| + 4e-7*iterations (tests/test_parity_gpu.py explains the second term).
 //
 // This translation unit is compiled with -fmad=false: every multiply-add that may fuse is written
 // as an explicit fma intrinsic.
@@ -169,28 +169,41 @@ struct FastMath {
         asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
         return y;
     }
-    // 2^((v - mx) * log2(e)) with the subtraction folded into one FFMA: mxl = -mx * log2(e)
-    static __device__ __forceinline__ float e(float v, float mxl)
+    // 2^((v - mx) * log2(e) + off).  The difference is taken first and exactly (FADD of nearby values):
+    // folding it into the FFMA as v * log2(e) - mx * log2(e) rounds at the magnitude of |u| and leaves a
+    // bias per update that accumulates with the distance from the goal (0.14 at u = -2000 on maze.png).
+    static __device__ __forceinline__ float e(float v, float mx, float off)
     {
-        return ex2(__fmaf_rn(v, 1.4426950408889634f, mxl));
+        return ex2(__fmaf_rn(__fsub_rn(v, mx), 1.4426950408889634f, off));
     }
     __device__ __forceinline__ float finish(float mx, float s) const
     {
         return __fsub_rn(__fmaf_rn(lg2(s), 0.6931471805599453f, mx), ln2n);
     }
+    // The largest neighbour contributes exactly 2^0 = 1, so only the other three need an ex2: a
+    // min/max network separates them (6 FMNMX) and saves one of the five MUFU operations per update --
+    // the MUFU pipe (16 lanes per SM and clock) is this mode's tightest resource.
+    //
+    // finish() keeps the reference's two rounding points at the magnitude of |u| -- float(mx + log(sum))
+    // and then "- log(2n)" -- on purpose.  Deep in a corridor u falls by a constant per cell, the
+    // roundings at |u| ~ 2^11 are as large as 1.2e-4 and repeat systematically from cell to cell, so an
+    // update with a different rounding sequence (e.g. folding log(2n) into the sum as sum/4, one rounding
+    // less) drifts away from the reference linearly with the distance from the goal: 0.14 at u = -2048
+    // on maps/maze.png, 14x the stated tolerance.  With the same rounding points the two agree to a few
+    // ulps (tests/test_parity_gpu.py::test_fast_mode_within_stated_tolerance).
     __device__ __forceinline__ float update4(float a, float b, float c, float d) const
     {
-        const float mx = fmaxf(fmaxf(a, b), fmaxf(c, d));
-        const float mxl = __fmul_rn(mx, -1.4426950408889634f);
-        const float s = __fadd_rn(__fadd_rn(e(a, mxl), e(b, mxl)), __fadd_rn(e(c, mxl), e(d, mxl)));
+        const float hi1 = fmaxf(a, b), lo1 = fminf(a, b);
+        const float hi2 = fmaxf(c, d), lo2 = fminf(c, d);
+        const float mx = fmaxf(hi1, hi2), mid = fminf(hi1, hi2);
+        const float s = __fadd_rn(__fadd_rn(e(lo1, mx, 0.0f), e(lo2, mx, 0.0f)), __fadd_rn(e(mid, mx, 0.0f), 1.0f));
         return finish(mx, s);
     }
     __device__ __forceinline__ float update6(float a, float b, float c, float d, float g, float f) const
     {
         const float mx = fmaxf(fmaxf(fmaxf(a, b), fmaxf(c, d)), fmaxf(g, f));
-        const float mxl = __fmul_rn(mx, -1.4426950408889634f);
-        const float s = __fadd_rn(__fadd_rn(__fadd_rn(e(a, mxl), e(b, mxl)), __fadd_rn(e(c, mxl), e(d, mxl))),
-                                  __fadd_rn(e(g, mxl), e(f, mxl)));
+        const float s = __fadd_rn(__fadd_rn(__fadd_rn(e(a, mx, 0.0f), e(b, mx, 0.0f)), __fadd_rn(e(c, mx, 0.0f), e(d, mx, 0.0f))),
+                                  __fadd_rn(e(g, mx, 0.0f), e(f, mx, 0.0f)));
         return finish(mx, s);
     }
 };

@@ -121,7 +121,7 @@ struct RowCtx {
     int T, TH, own_lo, own_hi;
     float dmax;
 
-    template <bool EVEN_COLS>
+    template <bool EVEN_COLS, bool CHECK>
     __device__ __forceinline__ void row(int r, const float4 &up, float4 &cur, const float4 &dn)
     {
         const uint32_t nib = lockt[r * kGroups + grp];
@@ -149,7 +149,7 @@ struct RowCtx {
             if (active & 2u) nw.y = ny;
             if (active & 8u) nw.w = nq;
         }
-        if (checking) {
+        if (CHECK && checking) {
             const int b = by0 + r;
             if (r >= T && r < TH - T && b >= own_lo && b < own_hi) {
                 // |prev - new| is 0 for cells that were not updated
@@ -165,6 +165,57 @@ struct RowCtx {
         }
         *reinterpret_cast<float4 *>(tile + r * kTileW + col) = nw;
         cur = nw;
+    }
+
+    __device__ __forceinline__ float4 load(int r) const
+    {
+        return *reinterpret_cast<const float4 *>(tile + r * kTileW + col);
+    }
+
+    // Rows [ra, rb) of one sweep.  Cell (r, c) is active when (pb + r + c) is odd; rows alternate between
+    // "even columns active" and "odd columns active", so the loop body is a pair of rows with the colour
+    // fixed at compile time.  a / b / c rotate roles (row above / row / row below) by renaming instead of
+    // by moves.  The check sweep (1 in 100) uses the compact loop only.
+    template <bool CHECK>
+    __device__ __forceinline__ void band(int ra, int rb, int pb)
+    {
+        float4 a = load(ra - 1), b = load(ra), c;
+        int r = ra;
+        if (((r + pb) & 1) == 0) {  // first row updates the odd columns: peel it
+            c = load(r + 1);
+            row<false, CHECK>(r, a, b, c);
+            a = b;
+            b = c;
+            ++r;
+        }
+        if (!CHECK) {
+            for (; r + 5 < rb; r += 6) {
+                c = load(r + 1);
+                row<true, CHECK>(r, a, b, c);
+                a = load(r + 2);
+                row<false, CHECK>(r + 1, b, c, a);
+                b = load(r + 3);
+                row<true, CHECK>(r + 2, c, a, b);
+                c = load(r + 4);
+                row<false, CHECK>(r + 3, a, b, c);
+                a = load(r + 5);
+                row<true, CHECK>(r + 4, b, c, a);
+                b = load(r + 6);
+                row<false, CHECK>(r + 5, c, a, b);
+            }
+        }
+        for (; r + 1 < rb; r += 2) {
+            c = load(r + 1);
+            row<true, CHECK>(r, a, b, c);
+            a = load(r + 2);
+            row<false, CHECK>(r + 1, b, c, a);
+            b = a;
+            a = c;
+        }
+        if (r < rb) {
+            c = load(r + 1);
+            row<true, CHECK>(r, a, b, c);
+        }
     }
 };
 
@@ -260,46 +311,10 @@ sweep2d_kernel(const __grid_constant__ CUtensorMap src_map, const Sweep2DParams 
         if (ra < rb) {
             RowCtx<Math> cx{math, tile, lockt, col, grp, lane, by0, checking && col_out, (int)p.T, (int)p.TH,
                             (int)p.own_lo, (int)p.own_hi, dmax};
-            float4 a = *reinterpret_cast<const float4 *>(tile + (ra - 1) * kTileW + col);
-            float4 b = *reinterpret_cast<const float4 *>(tile + ra * kTileW + col);
-            float4 c;
-            int r = ra;
-            // cell (r, c) is active when (it + x0 + x1) is odd  <=>  (pb + r + c) odd; rows alternate
-            // between "even columns active" and "odd columns active", so the loop body is a pair of rows
-            // with the colour fixed at compile time.  a / b / c rotate roles (row above / row / row below)
-            // by renaming instead of by moves.
-            if (((r + pb) & 1) == 0) {  // first row updates the odd columns: peel it
-                c = *reinterpret_cast<const float4 *>(tile + (r + 1) * kTileW + col);
-                cx.template row<false>(r, a, b, c);
-                a = b;
-                b = c;
-                ++r;
-            }
-            for (; r + 5 < rb; r += 6) {
-                c = *reinterpret_cast<const float4 *>(tile + (r + 1) * kTileW + col);
-                cx.template row<true>(r, a, b, c);
-                a = *reinterpret_cast<const float4 *>(tile + (r + 2) * kTileW + col);
-                cx.template row<false>(r + 1, b, c, a);
-                b = *reinterpret_cast<const float4 *>(tile + (r + 3) * kTileW + col);
-                cx.template row<true>(r + 2, c, a, b);
-                c = *reinterpret_cast<const float4 *>(tile + (r + 4) * kTileW + col);
-                cx.template row<false>(r + 3, a, b, c);
-                a = *reinterpret_cast<const float4 *>(tile + (r + 5) * kTileW + col);
-                cx.template row<true>(r + 4, b, c, a);
-                b = *reinterpret_cast<const float4 *>(tile + (r + 6) * kTileW + col);
-                cx.template row<false>(r + 5, c, a, b);
-            }
-            for (; r + 1 < rb; r += 2) {
-                c = *reinterpret_cast<const float4 *>(tile + (r + 1) * kTileW + col);
-                cx.template row<true>(r, a, b, c);
-                a = *reinterpret_cast<const float4 *>(tile + (r + 2) * kTileW + col);
-                cx.template row<false>(r + 1, b, c, a);
-                b = a;
-                a = c;
-            }
-            if (r < rb) {
-                c = *reinterpret_cast<const float4 *>(tile + (r + 1) * kTileW + col);
-                cx.template row<true>(r, a, b, c);
+            if (checking) {
+                cx.template band<true>(ra, rb, pb);
+            } else {
+                cx.template band<false>(ra, rb, pb);
             }
             dmax = cx.dmax;
         }
