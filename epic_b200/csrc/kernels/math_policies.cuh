@@ -83,7 +83,10 @@ struct StrictMath {
     // strict_expf_nonpos (strict_math.h), table split into 32-bit words.
     __device__ __forceinline__ float exp_nonpos(float x) const
     {
-        const double xd = (double)fmaxf(x, -104.5f);
+        // widening on the bit pattern (strict_widen_nonpos): two integer operations on lightly loaded
+        // pipes instead of one F2F.F64.F32 on the quarter-rate conversion pipe
+        const uint32_t xb = __float_as_uint(fmaxf(x, -104.5f));
+        const double xd = __hiloint2double((int)((xb >> 3) + 0xA8000000u), (int)(xb << 29));
         const double kdp = __fma_rn(inv_ln2n, xd, shift);
         const uint32_t ki = (uint32_t)__double2loint(kdp);
         const double kd = __dadd_rn(kdp, -shift);
@@ -106,7 +109,7 @@ struct StrictMath {
         const uint32_t iz = ix - (tmp & 0xff800000u);
         const double invc = __hiloint2double((int)t->invc_hi[i], (int)t->invc_lo[i]);
         const double y0 = __hiloint2double((int)t->y0_hi[ki], (int)t->y0_lo[ki]);
-        const double z = (double)__uint_as_float(iz);
+        const double z = __hiloint2double((int)((iz >> 3) + 0x38000000u), (int)(iz << 29));
         const double r = __fma_rn(z, invc, -1.0);
         double y = __fma_rn(a0, r, a1);
         y = __fma_rn(y, r, a2);
@@ -123,15 +126,32 @@ struct StrictMath {
         return __double2float_rn(__dadd_rn((double)t1, -log2n));
     }
 
-    // 2-D: neighbours in the reference's order (x0-1, x0+1, x1-1, x1+1).
+    // 2-D: neighbours in the reference's order (x0-1, x0+1, x1-1, x1+1); the reference sums
+    // ((E(a) + E(b)) + E(c)) + E(d) with E(v) = expf(v - max).
+    //
+    // The largest neighbour's term is expf(0) = 1 exactly, so three libm replays are enough: a min/max
+    // network finds the three losers (lo1, lo2, mid), their exponentials are evaluated, and selects put
+    // the terms back at the reference's positions.  E(a) + E(b) = E(max(a,b)) + E(min(a,b)) because a float
+    // add is commutative, so only the (c, d) pair needs its order restored.  Ties are harmless: a loser
+    // equal to the maximum goes through exp_nonpos(0) = 1.  (NaN, which the reference's std::max chain
+    // treats asymmetrically, is not reproduced -- as in exp_nonpos.)
     __device__ __forceinline__ float update4(float a, float b, float c, float d) const
     {
-        float mx = max_ref(a, b);
-        mx = max_ref(mx, c);
-        mx = max_ref(mx, d);
-        float s = __fadd_rn(exp_nonpos(__fsub_rn(a, mx)), exp_nonpos(__fsub_rn(b, mx)));
-        s = __fadd_rn(s, exp_nonpos(__fsub_rn(c, mx)));
-        s = __fadd_rn(s, exp_nonpos(__fsub_rn(d, mx)));
+        const float hi1 = fmaxf(a, b), lo1 = fminf(a, b);
+        const float hi2 = fmaxf(c, d), lo2 = fminf(c, d);
+        const float mx = fmaxf(hi1, hi2), mid = fminf(hi1, hi2);
+        const float e1 = exp_nonpos(__fsub_rn(lo1, mx));
+        const float e2 = exp_nonpos(__fsub_rn(lo2, mx));
+        const float em = exp_nonpos(__fsub_rn(mid, mx));
+        const bool p = hi1 < hi2;            // the maximum is in the (c, d) pair
+        const float eh1 = p ? em : 1.0f;     // E(max(a, b))
+        const float eh2 = p ? 1.0f : em;     // E(max(c, d))
+        const bool q = c < d;
+        const float ec = q ? e2 : eh2;
+        const float ed = q ? eh2 : e2;
+        float s = __fadd_rn(eh1, e1);
+        s = __fadd_rn(s, ec);
+        s = __fadd_rn(s, ed);
         return finish(mx, s);
     }
 

@@ -146,12 +146,26 @@ EPIC_HD float strict_from_fbits(uint32_t b)
 //     2^-149 results), and
 //   * the polynomial in Horner form with s folded in, s + (s*r) * ((C0*r + C1)*r + C2), needs 7 double
 //     operations instead of 8
+//   * the float -> double widening of x done on the bit pattern (exponent rebias + shift; exact for
+//     every normal x, while +-0 and denormals turn into negative numbers below 2^-126 in magnitude, for
+//     which the result is the same 1.0f) -- on the GPU this moves the conversion off the quarter-rate
+//     conversion pipe (F2F.F64.F32), the busiest pipe of the strict sweep,
 // give the same float as glibc for every x <= 0.  NaN is not reproduced bit for bit (payload).
+EPIC_HD double strict_widen_nonpos(float xc)
+{
+    const uint32_t b = strict_fbits(xc);
+    // x <= 0 has the sign bit set: (b >> 3) carries it into bit 28, and 0x10000000 + 0xA8000000 = 0xB8000000
+    // = sign | (1023 - 127) << 20.  (x == +0 becomes -2^-383: same result, 1.0f.)
+    const uint32_t hi = (b >> 3) + 0xA8000000u;
+    const uint32_t lo = b << 29;
+    return strict_from_bits(((uint64_t)hi << 32) | lo);
+}
+
 template <typename Table>
 EPIC_HD float strict_expf_nonpos(float x, const Table &tab)
 {
     const float xc = (x < -104.5f) ? -104.5f : x;
-    const double xd = (double)xc;
+    const double xd = strict_widen_nonpos(xc);
     const double kdp = strict_fma(kExpInvLn2N, xd, kExpShift);   // z + SHIFT, contracted
     const uint64_t ki = strict_bits(kdp);
     const double kd = strict_add(kdp, -kExpShift);
@@ -177,7 +191,8 @@ EPIC_HD float strict_logf_normal(float x, const Table &tab)
     const int32_t k = (int32_t)tmp >> 23;
     const uint32_t iz = ix - (tmp & 0xff800000u);
     const double invc = tab[2 * i], logc = tab[2 * i + 1];
-    const double z = (double)strict_from_fbits(iz);
+    // z is a normal positive float: widening on the bit pattern is exact
+    const double z = strict_from_bits(((uint64_t)((iz >> 3) + 0x38000000u) << 32) | (uint32_t)(iz << 29));
     const double r = strict_fma(z, invc, -1.0);
     const double y0 = strict_fma((double)k, kLogLn2, logc);
     double y = strict_fma(kLogA0, r, kLogA1);

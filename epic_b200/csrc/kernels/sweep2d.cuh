@@ -322,22 +322,33 @@ sweep2d_kernel(const __grid_constant__ CUtensorMap src_map, const Sweep2DParams 
     }
 
     // Write the output region (all of it, locked cells included: dst is a different buffer).
+    // A warp stores whole rows (lane = float4 group, two groups per lane): no per-item index arithmetic.
     {
-        const int ogroups = (int)p.out_w / 4;
-        const int items = (int)p.out_h * ogroups;
-        for (int item = tid; item < items; item += NT) {
-            const int r = (int)p.T + item / ogroups;
-            const int c = (int)p.HC + (item % ogroups) * 4;
+        const int r_end = min((int)p.TH - (int)p.T, (int)p.own_hi - by0);
+        const int c_end = min(kTileW - (int)p.HC, (int)p.pitch - gx0);
+        for (int r = max((int)p.T, (int)p.own_lo - by0) + warp; r < r_end; r += NT / 32) {
             const int b = by0 + r;
-            const int gx = gx0 + c;
-            if (b >= (int)p.own_lo && b < (int)p.own_hi && gx < (int)p.pitch) {
-                const float4 v = *reinterpret_cast<const float4 *>(tile + r * kTileW + c);
-                *reinterpret_cast<float4 *>(p.dst + (size_t)b * p.pitch + gx) = v;
-                if (p.peer_up != nullptr && b < (int)(p.own_lo + p.halo_rows)) {
-                    *reinterpret_cast<float4 *>(p.peer_up + (size_t)(b - (int)p.own_lo) * p.pitch + gx) = v;
-                }
-                if (p.peer_down != nullptr && b >= (int)(p.own_hi - p.halo_rows)) {
-                    *reinterpret_cast<float4 *>(p.peer_down + (size_t)(b - (int)(p.own_hi - p.halo_rows)) * p.pitch + gx) = v;
+            const float *trow = tile + r * kTileW;
+            float *drow = p.dst + (size_t)b * p.pitch + gx0;
+            float *urow = nullptr, *lrow = nullptr;
+            if (p.peer_up != nullptr && b < (int)(p.own_lo + p.halo_rows)) {
+                urow = p.peer_up + (size_t)(b - (int)p.own_lo) * p.pitch + gx0;
+            }
+            if (p.peer_down != nullptr && b >= (int)(p.own_hi - p.halo_rows)) {
+                lrow = p.peer_down + (size_t)(b - (int)(p.own_hi - p.halo_rows)) * p.pitch + gx0;
+            }
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int c = (int)p.HC + lane * 4 + k * 128;
+                if (c < c_end) {
+                    const float4 v = *reinterpret_cast<const float4 *>(trow + c);
+                    *reinterpret_cast<float4 *>(drow + c) = v;
+                    if (urow != nullptr) {
+                        *reinterpret_cast<float4 *>(urow + c) = v;
+                    }
+                    if (lrow != nullptr) {
+                        *reinterpret_cast<float4 *>(lrow + c) = v;
+                    }
                 }
             }
         }

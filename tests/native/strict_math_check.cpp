@@ -25,6 +25,10 @@ int main(int argc, char **argv)
             bad_e++;
         }
     }
+    if (strict_fbits(strict_expf_nonpos(0.0f, kT)) != strict_fbits(expf(0.0f))) {  // +0 (a == max neighbour)
+        printf("expf(+0) differs\n");
+        bad_e++;
+    }
     // every normal x in [2^-3, 2^4): covers the sweep's [1, 6]
 #pragma omp parallel for reduction(+ : bad_l, n_l) schedule(static)
     for (long long b = 0x3e000000ll; b < 0x41800000ll; b += stride) {
