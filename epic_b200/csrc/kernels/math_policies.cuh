@@ -22,8 +22,9 @@ namespace epic_b200 {
 struct MathTables {
     uint32_t exp_hi[32];
     uint32_t exp_lo[32];
-    uint32_t invc_hi[16];
-    uint32_t invc_lo[16];
+    // invc[k*16 + i] = invc[i] * 2^-k (exact), see strict_logf_sum in strict_math.h
+    uint32_t invc_hi[64];
+    uint32_t invc_lo[64];
     // y0[k*16 + i] = fma(k, Ln2, logc[i]) for k = 0..3: the log argument is a sum of 2n <= 6 terms in
     // [1, 6], for which glibc's exponent k is 0..3, so its first FMA (and the int -> double conversion
     // of k) becomes a lookup of the identical double.
@@ -40,12 +41,10 @@ __device__ __forceinline__ void load_math_tables(MathTables *t, int tid, int nth
         t->exp_hi[i] = (uint32_t)(c_exp2f_table[i] >> 32);
         t->exp_lo[i] = (uint32_t)c_exp2f_table[i];
     }
-    for (int i = tid; i < 16; i += nthreads) {
-        const uint64_t a = (uint64_t)__double_as_longlong(c_logf_table[2 * i]);
+    for (int i = tid; i < 64; i += nthreads) {
+        const uint64_t a = (uint64_t)__double_as_longlong(c_logf_table[2 * (i & 15)]) - ((uint64_t)(i >> 4) << 52);
         t->invc_hi[i] = (uint32_t)(a >> 32);
         t->invc_lo[i] = (uint32_t)a;
-    }
-    for (int i = tid; i < 64; i += nthreads) {
         const double y0 = __fma_rn((double)(i >> 4), kLogLn2, c_logf_table[2 * (i & 15) + 1]);
         const uint64_t b = (uint64_t)__double_as_longlong(y0);
         t->y0_hi[i] = (uint32_t)(b >> 32);
@@ -99,18 +98,15 @@ struct StrictMath {
         return __double2float_rn(__fma_rn(y, sr, s));
     }
 
-    // strict_logf_normal (strict_math.h) for x in [1, 2n], y0 from the (k, i) table.
+    // strict_logf_sum (strict_math.h) for x in [1, 2n]: both table operands indexed by (k, i).
     __device__ __forceinline__ float log_sum(float x) const
     {
         const uint32_t ix = __float_as_uint(x);
-        const uint32_t tmp = ix - 0x3f330000u;
-        const uint32_t ki = (tmp >> 19) & 63u;   // k * 16 + i, k <= 3
-        const uint32_t i = ki & 15u;
-        const uint32_t iz = ix - (tmp & 0xff800000u);
-        const double invc = __hiloint2double((int)t->invc_hi[i], (int)t->invc_lo[i]);
+        const uint32_t ki = ((ix - 0x3f330000u) >> 19) & 63u;   // k * 16 + i, k <= 3
+        const double invc = __hiloint2double((int)t->invc_hi[ki], (int)t->invc_lo[ki]);
         const double y0 = __hiloint2double((int)t->y0_hi[ki], (int)t->y0_lo[ki]);
-        const double z = __hiloint2double((int)((iz >> 3) + 0x38000000u), (int)(iz << 29));
-        const double r = __fma_rn(z, invc, -1.0);
+        const double xd = __hiloint2double((int)((ix >> 3) + 0x38000000u), (int)(ix << 29));
+        const double r = __fma_rn(xd, invc, -1.0);
         double y = __fma_rn(a0, r, a1);
         y = __fma_rn(y, r, a2);
         y = __fma_rn(y, r, 1.0);

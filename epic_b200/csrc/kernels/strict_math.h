@@ -201,4 +201,27 @@ EPIC_HD float strict_logf_normal(float x, const Table &tab)
     return (float)strict_fma(y, r, y0);
 }
 
+// The sweep's logf argument is a sum of 2n <= 6 terms, each <= 1 and one of them == 1: x in [1, 6], where
+// glibc's exponent k is 0..3.  For that range the two table operands can be indexed by (k, i) together:
+//   y0[k*16 + i]   = fma(k, Ln2, logc[i])   (the identical double glibc computes first), and
+//   invc[i] * 2^-k (exact), so that r = fma(x, invc*2^-k, -1) is glibc's fma(z, invc, -1) with z = x*2^-k
+// without forming z.  This is the form the device code uses (math_policies.cuh, StrictMath::log_sum);
+// checked exhaustively over [1, 8) like the functions above.
+template <typename Table>
+EPIC_HD float strict_logf_sum(float x, const Table &tab)
+{
+    const uint32_t ix = strict_fbits(x);
+    const uint32_t tmp = ix - 0x3f330000u;
+    const uint32_t ki = (tmp >> 19) & 63u;   // k * 16 + i
+    const uint32_t i = ki & 15u, k = ki >> 4;
+    const double invc_k = strict_from_bits(strict_bits(tab[2 * i]) - ((uint64_t)k << 52));
+    const double y0 = strict_fma((double)k, kLogLn2, tab[2 * i + 1]);
+    const double xd = strict_from_bits(((uint64_t)((ix >> 3) + 0x38000000u) << 32) | (uint32_t)(ix << 29));
+    const double r = strict_fma(xd, invc_k, -1.0);
+    double y = strict_fma(kLogA0, r, kLogA1);
+    y = strict_fma(y, r, kLogA2);
+    y = strict_fma(y, r, 1.0);
+    return (float)strict_fma(y, r, y0);
+}
+
 }  // namespace epic_b200

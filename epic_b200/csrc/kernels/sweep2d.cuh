@@ -233,7 +233,11 @@ sweep2d_kernel(const __grid_constant__ CUtensorMap src_map, const Sweep2DParams 
     uint64_t *bar = reinterpret_cast<uint64_t *>(tables + 1);
     float *s_red = reinterpret_cast<float *>(bar + 1);
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    // read through a shuffle so that the compiler knows the warp index is warp-uniform: band limits and loop
+    // trip counts then live in uniform registers and the warp-synchronous operations in the row loop need
+    // no convergence checks
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int tx = blockIdx.x % p.ntx, ty = blockIdx.x / p.ntx;
     const int gx0 = tx * (int)p.out_w - (int)p.HC;                 // grid column of tile column 0
     const int by0 = (int)p.own_lo + ty * (int)p.out_h - (int)p.T;  // buffer row of tile row 0
