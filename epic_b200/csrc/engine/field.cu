@@ -167,14 +167,29 @@ int Field::create(Field **out, unsigned n, const uint64_t *gm, uint64_t row0, ui
     f->own_lo_ = ghost;
     f->own_hi_ = ghost + rows;
     const uint64_t inner = gm[n - 1];
-    f->pitch_ = std::max<uint64_t>(round_up(inner, 32), (n == 2) ? (uint64_t)kTileW : 32ull);
+    f->pitch_ = std::max<uint64_t>(round_up(inner, 32), (n == 2) ? (uint64_t)kTileW : (uint64_t)k3W);
     f->mask_wpr_ = f->pitch_ / 32;
     f->layer_floats_ = (n == 2) ? f->pitch_ : gm[1] * f->pitch_;
 
     // Tile geometry (2-D): the largest tile that still gives every SM a CTA.
-    f->T_ = (n == 2) ? 4 : 1;
+    f->T_ = (n == 2) ? 4 : k3HR;
     if (cfg.sweeps_per_pass > 0 && n == 2) {
         f->T_ = std::min(cfg.sweeps_per_pass, 8);
+    }
+    if (n == 3) {
+        // 3-D: a column of BH x 128 tiles walked along x0 (sweep3d.cuh); BH rows include 2 halo rows per side
+        f->TH_ = 34;
+        if (cfg.tile_rows >= 8 && cfg.tile_rows <= 40 && cfg.tile_rows % 2 == 0) {
+            f->TH_ = cfg.tile_rows;
+        }
+        f->NT_ = k3Threads;
+        const size_t smem = sweep3d_smem_bytes((uint32_t)f->TH_);
+        if (!allow_smem(sweep3d_kernel<StrictMath>, smem) || !allow_smem(sweep3d_kernel<FastMath>, smem)) {
+            cudaGetLastError();
+            delete f;
+            return kInvalidCudaParam;
+        }
+        f->attr_done_ = true;
     }
     if (n == 2) {
         // Tile geometry: estimate the time of one pass for every candidate (threads, tile rows) and keep
@@ -242,12 +257,12 @@ int Field::create(Field **out, unsigned n, const uint64_t *gm, uint64_t row0, ui
 
     // Device memory.  The 2-D buffers are padded to at least one tile so a TMA box never exceeds
     // the tensor it reads from.
-    const uint64_t alloc_layers = (n == 2) ? std::max<uint64_t>(f->buf_layers_, 256) : f->buf_layers_;
+    const uint64_t alloc_layers = f->alloc_layers();
     const size_t ubytes = (size_t)alloc_layers * f->layer_floats_ * sizeof(float);
     const uint64_t mask_rows = (n == 2) ? alloc_layers : alloc_layers * gm[1];
     const size_t mbytes = (size_t)mask_rows * f->mask_wpr_ * sizeof(uint32_t);
     bool ok = true;
-    const int nbuf = (n == 2) ? 2 : 1;  // the 3-D sweep runs in place
+    const int nbuf = 2;
     for (int i = 0; i < nbuf && ok; ++i) {
         ok = cudaMalloc(&f->u_[i], ubytes) == cudaSuccess && cudaMemset(f->u_[i], 0, ubytes) == cudaSuccess;
     }
@@ -274,7 +289,7 @@ int Field::create(Field **out, unsigned n, const uint64_t *gm, uint64_t row0, ui
         delete f;
         return kDeviceMalloc;
     }
-    if (n == 2) {
+    {
         const int r = f->build_tensor_maps();
         if (r != kSuccess) {
             delete f;
@@ -319,11 +334,12 @@ int Field::build_tensor_maps()
         fprintf(stderr, "Error[epic_b200]: cuTensorMapEncodeTiled is not available from the driver.\n");
         return kInvalidCudaParam;
     }
-    const uint64_t alloc_layers = std::max<uint64_t>(buf_layers_, 256);
+    // 3-D fields are presented as a 2-D tensor of pitch x (layers * m1) rows: a box is one layer-tile
+    const uint64_t tensor_rows = (n_ == 2) ? alloc_layers() : alloc_layers() * gm_[1];
     for (int i = 0; i < 2; ++i) {
-        cuuint64_t gdim[2] = {(cuuint64_t)pitch_, (cuuint64_t)alloc_layers};
+        cuuint64_t gdim[2] = {(cuuint64_t)pitch_, (cuuint64_t)tensor_rows};
         cuuint64_t gstride[1] = {(cuuint64_t)pitch_ * sizeof(float)};
-        cuuint32_t box[2] = {(cuuint32_t)kTileW, (cuuint32_t)TH_};
+        cuuint32_t box[2] = {(cuuint32_t)((n_ == 2) ? kTileW : k3W), (cuuint32_t)TH_};
         cuuint32_t estride[2] = {1, 1};
         const CUresult r = enc(&tmap_[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, u_[i], gdim, gstride, box, estride,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -504,7 +520,7 @@ int Field::peer_export(PeerInfo *out)
     }
     DeviceGuard guard(cfg_.device);
     memset(out, 0, sizeof(*out));
-    const int nbuf = (n_ == 2) ? 2 : 1;
+    const int nbuf = 2;
     for (int i = 0; i < nbuf; ++i) {
         if (cudaIpcGetMemHandle(&out->u[i], u_[i]) != cudaSuccess) {
             cudaGetLastError();
@@ -535,7 +551,7 @@ int Field::set_peer_ipc(int dir, const PeerInfo *info)
         return kInvalidCudaParam;
     }
     Peer &p = peer_[dir];
-    const int nbuf = (n_ == 2) ? 2 : 1;
+    const int nbuf = 2;
     bool ok = true;
     for (int i = 0; i < nbuf && ok; ++i) {
         ok = cudaIpcOpenMemHandle((void **)&p.u[i], info->u[i], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
@@ -713,55 +729,82 @@ int Field::launch_pass_2d(uint32_t it0, uint32_t count, bool check_last)
 
 int Field::launch_pass_3d(uint32_t it0, uint32_t count, bool check_last)
 {
-    for (uint32_t s = 0; s < count; ++s) {
-        Sweep3DParams p;
-        memset(&p, 0, sizeof(p));
-        p.u = u_[cur_];
-        p.freemask = freemask_;
-        p.ctrl_done = &ctrl_->done;
-        p.delta_bits = &ctrl_->delta_bits;
-        p.pitch = pitch_;
-        p.layer_floats = layer_floats_;
-        p.mask_wpr = (uint32_t)mask_wpr_;
-        p.m0 = (uint32_t)gm_[0];
-        p.m1 = (uint32_t)gm_[1];
-        p.m2 = (uint32_t)gm_[2];
-        p.grow0 = grow0_;
-        p.own_lo = (uint32_t)own_lo_;
-        p.own_hi = (uint32_t)own_hi_;
-        p.segs = (uint32_t)((pitch_ + 127) / 128);
-        p.row_blocks = (uint32_t)((gm_[1] + 7) / 8);
-        p.it = it0 + s;
-        p.check = (check_last && s + 1 == count) ? 1u : 0u;
-        if (peer_[0].on) {
-            p.peer_up = peer_[0].u[0] + peer_[0].own_hi * layer_floats_;
+    Sweep3DParams p;
+    memset(&p, 0, sizeof(p));
+    p.dst = u_[cur_ ^ 1];
+    p.freemask = freemask_;
+    p.ctrl_done = &ctrl_->done;
+    p.delta_bits = &ctrl_->delta_bits;
+    p.pitch = pitch_;
+    p.layer_floats = layer_floats_;
+    p.mask_wpr = (uint32_t)mask_wpr_;
+    p.m0 = (uint32_t)gm_[0];
+    p.m1 = (uint32_t)gm_[1];
+    p.m2 = (uint32_t)gm_[2];
+    p.grow0 = grow0_;
+    p.buf_layers = (uint32_t)buf_layers_;
+    p.own_lo = (uint32_t)own_lo_;
+    p.own_hi = (uint32_t)own_hi_;
+    p.BH = (uint32_t)TH_;
+    p.ntx = (uint32_t)((gm_[2] + k3OutW - 1) / k3OutW);
+    p.nty = (uint32_t)((gm_[1] + (p.BH - 2 * k3HR) - 1) / (p.BH - 2 * k3HR));
+    // Layers per CTA: a CTA costs (its layers + the 2 * 2 halo layers); the grid runs in waves of two CTAs
+    // per SM.  Take the split along x0 with the cheapest estimated pass.
+    {
+        const uint64_t tiles_xy = (uint64_t)p.ntx * p.nty;
+        const uint64_t slots = 2ull * (uint64_t)sms_;
+        uint64_t best_cost = 0;
+        uint32_t best_chunk = (uint32_t)rows_;
+        const uint64_t max_ntz = std::max<uint64_t>(1, std::min<uint64_t>(256, rows_ / 4));
+        for (uint64_t ntz = 1; ntz <= max_ntz; ++ntz) {
+            const uint64_t chunk = (rows_ + ntz - 1) / ntz;
+            const uint64_t ctas = tiles_xy * ((rows_ + chunk - 1) / chunk);
+            const uint64_t cost = ((ctas + slots - 1) / slots) * (chunk + 2 * k3HR + 2);
+            if (best_cost == 0 || cost < best_cost) {
+                best_cost = cost;
+                best_chunk = (uint32_t)chunk;
+            }
         }
-        if (peer_[1].on) {
-            p.peer_down = peer_[1].u[0] + (peer_[1].own_lo - 1) * layer_floats_;
-        }
-        if (wait_peers() != kSuccess) {
-            return kKernelExecution;
-        }
-        const uint64_t work = (uint64_t)rows_ * p.row_blocks * p.segs;
-        const uint32_t grid = (uint32_t)std::min<uint64_t>(work, (uint64_t)sms_ * 3);
-        if (cfg_.math == MATH_STRICT) {
-            StrictMath m;
-            m.init(kLog6);
-            sweep3d_kernel<StrictMath><<<grid, 256, 0, stream_>>>(p, m);
-        } else {
-            FastMath m;
-            m.ln2n = 1.791759469228055f;
-            sweep3d_kernel<FastMath><<<grid, 256, 0, stream_>>>(p, m);
-        }
-        launches_++;
-        if (cudaGetLastError() != cudaSuccess) {
-            return kKernelExecution;
-        }
-        if (signal_peers() != kSuccess) {
-            return kKernelExecution;
-        }
+        p.zchunk = best_chunk;
     }
-    return kSuccess;
+    const uint32_t ntz = (uint32_t)((rows_ + p.zchunk - 1) / p.zchunk);
+    p.count = count;
+    p.it0 = it0;
+    p.check = check_last ? 1u : 0u;
+    p.halo_layers = (uint32_t)std::min<uint64_t>(ghost_, rows_);
+    if (peer_[0].on) {
+        p.peer_up = peer_[0].u[cur_ ^ 1] + peer_[0].own_hi * layer_floats_;
+    }
+    if (peer_[1].on) {
+        p.peer_down = peer_[1].u[cur_ ^ 1] + (peer_[1].own_lo - p.halo_layers) * layer_floats_;
+    }
+    if (wait_peers() != kSuccess) {
+        return kKernelExecution;
+    }
+    const size_t smem = sweep3d_smem_bytes(p.BH);
+    if (!attr_done_) {  // per device, so per field
+        if (!allow_smem(sweep3d_kernel<StrictMath>, smem) || !allow_smem(sweep3d_kernel<FastMath>, smem)) {
+            cudaGetLastError();
+            return kInvalidCudaParam;
+        }
+        attr_done_ = true;
+    }
+    const uint32_t grid = p.ntx * p.nty * ntz;
+    if (cfg_.math == MATH_STRICT) {
+        StrictMath m;
+        m.init(kLog6);
+        sweep3d_kernel<StrictMath><<<grid, k3Threads, smem, stream_>>>(tmap_[cur_], p, m);
+    } else {
+        FastMath m;
+        m.ln2n = 1.791759469228055f;
+        sweep3d_kernel<FastMath><<<grid, k3Threads, smem, stream_>>>(tmap_[cur_], p, m);
+    }
+    launches_++;
+    if (cudaGetLastError() != cudaSuccess) {
+        return kKernelExecution;
+    }
+    cur_ ^= 1;
+    return signal_peers();
 }
 
 int Field::launch_pass(uint32_t it0, uint32_t count, bool check_last)

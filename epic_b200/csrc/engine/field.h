@@ -120,6 +120,15 @@ public:
 
 private:
     Field() {}
+    // Layers allocated per buffer: padded so that a TMA box never exceeds the tensor it reads from.
+    uint64_t alloc_layers() const
+    {
+        if (n_ == 2) {
+            return buf_layers_ > 256 ? buf_layers_ : 256;
+        }
+        const uint64_t need = (64 + gm_[1] - 1) / gm_[1];   // at least 64 rows of pitch floats
+        return buf_layers_ > need ? buf_layers_ : need;
+    }
     int build_tensor_maps();
     int launch_pass(uint32_t it0, uint32_t count, bool check_last);
     int launch_pass_2d(uint32_t it0, uint32_t count, bool check_last);

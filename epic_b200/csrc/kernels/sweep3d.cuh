@@ -1,4 +1,4 @@
-// sweep3d.cuh -- red-black log-sum-exp half-sweep, 3-D (6 neighbours).
+// sweep3d.cuh -- temporally blocked red-black log-sum-exp sweep, 3-D (6 neighbours).
 //
 // The reference has no GPU kernel for n = 3 (harmonic_gpu.cu:334-336, :367-369 are empty branches);
 // the semantics are those of the CPU path, harmonic_update_3d_cpu (harmonic_cpu.cpp:81-133):
@@ -6,23 +6,42 @@
 // skipped, the six neighbours enter the max and the sum in the order x0-1, x0+1, x1-1, x1+1,
 // x2-1, x2+1, and delta is the max |u_prev - u_new| over the cells of the check sweep's colour.
 //
-// One half-sweep per launch, in place (a red-black half-sweep only reads the other colour, so
-// there is no hazard).  A warp owns 128 consecutive x2 cells of one (x0, x1) pencil, one float4 per
-// lane; the x2 neighbours that fall into the adjacent lane come by shuffle.  A CTA covers 8
-// adjacent x1 rows so that the x1-1 / x1+1 rows are L1 hits, and consecutive CTAs walk x1 then x0
-// so that the x0-1 / x0+1 planes are L2 hits: DRAM sees each cell once per sweep for reading and
-// once for writing.
+// One pass = up to T = 2 consecutive half-sweeps (one of each colour) from the source buffer into the
+// destination buffer.  A CTA owns a column of the grid: an (x1, x2) tile of BH x 128 cells (halo: 2
+// rows and 4 columns on each side) and walks along x0 through a chunk of layers, keeping a ring of six
+// layer-tiles in shared memory.  Each tile arrives by one TMA box load (the field is presented to the
+// TMA unit as a 2-D tensor of pitch x (layers * m1), so rows outside the grid come from the
+// neighbouring layer or are zero-filled; they only ever feed cells whose results are masked).  At
+// step s the CTA
+//     sweeps colour A (iteration it0) on layer s       -- reads layers s-1, s, s+1,
+//     sweeps colour B (iteration it0 + 1) on layer s-1 -- reads layers s-2, s-1, s, all of which have
+//                                                         had their colour-A sweep,
+//     writes layer s-1 (now two iterations ahead) to the destination buffer, and
+//     has the loads of layers s+2 and s+3 in flight.
+// DRAM sees every cell once for reading (plus the halo overlap) and once for writing per TWO
+// half-sweeps; the per-launch work is the same arithmetic as the 2-D kernel with two more
+// neighbours.  With count == 1 only the colour-A sweep runs and layer s is written.
 #pragma once
 
+#include <cuda.h>
 #include <stdint.h>
 
 #include "math_policies.cuh"
+#include "sweep2d.cuh"   // mbarrier / TMA helpers
 
 namespace epic_b200 {
 
+constexpr int k3W = 128;       // tile columns (x2): one float4 per lane
+constexpr int k3G = k3W / 4;   // float4 groups per tile row
+constexpr int k3Slots = 6;     // layer-tiles resident in shared memory
+constexpr int k3HC = 4;        // halo columns on each side (float4 alignment; 2 would do)
+constexpr int k3HR = 2;        // halo rows / layers on each side = sweeps per pass
+constexpr int k3OutW = k3W - 2 * k3HC;
+constexpr int k3Threads = 256;
+
 struct Sweep3DParams {
-    float *u;                  // current buffer, buffer layer 0
-    const uint32_t *freemask;  // 1 bit per cell, buffer layout
+    float *dst;                // destination buffer, buffer layer 0
+    const uint32_t *freemask;  // 1 bit per cell, buffer layout (rows = layer * m1 + x1)
     const uint32_t *ctrl_done;
     uint32_t *delta_bits;
     uint64_t pitch;            // floats per x2 row
@@ -30,132 +49,305 @@ struct Sweep3DParams {
     uint32_t mask_wpr;         // mask words per x2 row
     uint32_t m0, m1, m2;       // global dimensions
     int64_t grow0;             // global x0 of buffer layer 0
-    uint32_t own_lo, own_hi;   // buffer layers updated by this slab
-    uint32_t segs;             // 128-cell segments per x2 row
-    uint32_t row_blocks;       // ceil(m1 / 8)
-    uint32_t it;               // iteration (colour)
-    uint32_t check;
-    // peer-to-peer halos (sharded runs): new values of the first / last owned layer are also stored
-    // into the neighbouring GPU's ghost layer
-    float *peer_up;            // the upper neighbour's ghost-below layer
-    float *peer_down;          // the lower neighbour's ghost-above layer
+    uint32_t buf_layers;       // layers present in the buffer
+    uint32_t own_lo, own_hi;   // buffer layers written by this slab
+    uint32_t BH;               // tile rows (x1) including the halo
+    uint32_t ntx, nty;         // tiles along x2 and x1
+    uint32_t zchunk;           // owned layers per CTA
+    uint32_t count;            // half-sweeps in this pass: 1 or 2
+    uint32_t it0;              // iteration of the first one
+    uint32_t check;            // the last sweep of the pass accumulates delta
+    // peer-to-peer halos (sharded runs): the first / last `halo_layers` owned layers are also stored
+    // into the neighbouring GPU's ghost layers (in ITS destination buffer)
+    float *peer_up;            // layer 0 of the upper neighbour's ghost-below region
+    float *peer_down;          // layer 0 of the lower neighbour's ghost-above region
+    uint32_t halo_layers;
 };
 
-template <class Math>
-__global__ void __launch_bounds__(256, 3)
-sweep3d_kernel(const Sweep3DParams p, const Math math_in)
+// [6 layer-tiles][6 nibble tiles][MathTables][6 mbarriers][8 warp maxima]
+inline size_t sweep3d_smem_bytes(uint32_t BH)
 {
-    if (*p.ctrl_done) {
-        return;
-    }
-    __shared__ MathTables tables;
-    __shared__ float s_red[8];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    load_math_tables(&tables, tid, 256);
-    __syncthreads();
-    Math math = math_in;
-    math.bind(&tables);
+    return (size_t)k3Slots * BH * k3W * sizeof(float) + (size_t)k3Slots * BH * k3G + sizeof(MathTables) +
+           k3Slots * 8 + 8 * sizeof(float);
+}
 
-    float dmax = 0.0f;
-    const uint64_t per_layer = (uint64_t)p.row_blocks * p.segs;
-    const uint64_t total = (uint64_t)(p.own_hi - p.own_lo) * per_layer;
-    for (uint64_t w = blockIdx.x; w < total; w += gridDim.x) {
-        const uint32_t b0 = p.own_lo + (uint32_t)(w / per_layer);
-        const uint32_t rem = (uint32_t)(w % per_layer);
-        const uint32_t x1 = (rem / p.segs) * 8u + (uint32_t)warp;
-        const uint32_t x2 = (rem % p.segs) * 128u + (uint32_t)lane * 4u;
-        const int64_t x0 = p.grow0 + (int64_t)b0;
-        if (x0 <= 0 || x0 >= (int64_t)p.m0 - 1 || x1 == 0 || x1 >= p.m1 - 1) {
-            continue;  // warp-uniform: a whole pencil on the global border
-        }
-        // free bits of this lane's four cells, border columns removed (lanes past the row: none)
-        const uint64_t row = (uint64_t)b0 * p.m1 + x1;
-        uint32_t nib = 0u;
-        if (x2 < p.pitch) {
-            nib = (__ldg(p.freemask + row * p.mask_wpr + (x2 >> 5)) >> (x2 & 31u)) & 0xFu;
-            if (x2 == 0) {
-                nib &= ~1u;
-            }
-            if (x2 + 4 > p.m2 - 1) {  // some of x2..x2+3 are >= m2-1
-                const uint32_t keep = (p.m2 - 1 > x2) ? (p.m2 - 1 - x2) : 0u;  // cells below m2-1
-                nib &= (1u << keep) - 1u;
-            }
-        }
-        // active colour: (it + x0 + x1 + x2) even
-        const bool even_cols = (((uint32_t)(p.it + (uint32_t)x0 + x1)) & 1u) == 0u;
-        const uint32_t active = even_cols ? (nib & 0x5u) : (nib & 0xAu);
+__device__ __forceinline__ void fence_proxy_async_smem()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+template <class Math>
+struct Rows3D {
+    const Math &math;
+    int lane;
+    float dmax;
+
+    static __device__ __forceinline__ float4 ld(const float *plane, int r, int lane)
+    {
+        return *reinterpret_cast<const float4 *>(plane + r * k3W + lane * 4);
+    }
+
+    // One tile row: `b` = this row (updated in place), a / c = rows r-1 / r+1 of the same layer,
+    // pm / pp = the layers below / above.  EVEN: the columns 0, 2 of each float4 are the active colour.
+    template <bool EVEN, bool CHECK>
+    __device__ __forceinline__ void row(float *pc, const float *pm, const float *pp, const uint8_t *mk, int r,
+                                        const float4 &a, float4 &b, const float4 &c, bool chk)
+    {
+        const uint32_t nib = mk[r * k3G + lane];
+        const uint32_t active = EVEN ? (nib & 0x5u) : (nib & 0xAu);
         if (!__any_sync(0xffffffffu, active != 0u)) {
-            continue;
+            return;
         }
-        const bool in_row = x2 < p.pitch;
-        float *c = p.u + (uint64_t)b0 * p.layer_floats + (uint64_t)x1 * p.pitch + (in_row ? x2 : 0u);
-        const float4 zero4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        const float4 cur = in_row ? *reinterpret_cast<const float4 *>(c) : zero4;
-        const float4 a0 = in_row ? *reinterpret_cast<const float4 *>(c - p.layer_floats) : zero4;
-        const float4 a1 = in_row ? *reinterpret_cast<const float4 *>(c + p.layer_floats) : zero4;
-        const float4 b0v = in_row ? *reinterpret_cast<const float4 *>(c - p.pitch) : zero4;
-        const float4 b1v = in_row ? *reinterpret_cast<const float4 *>(c + p.pitch) : zero4;
-        float4 nw = cur;
-        if (even_cols) {
-            float left = __shfl_up_sync(0xffffffffu, cur.w, 1);
-            if (lane == 0 && x2 > 0) {
-                left = c[-1];
-            }
-            const float nx = math.update6(a0.x, a1.x, b0v.x, b1v.x, left, cur.y);
-            const float nz = math.update6(a0.z, a1.z, b0v.z, b1v.z, cur.y, cur.w);
+        const float4 m = ld(pm, r, lane), q = ld(pp, r, lane);
+        float4 nw = b;
+        if (EVEN) {
+            // lane 0's left neighbour is outside the tile: its column 0 is never active
+            const float left = __shfl_up_sync(0xffffffffu, b.w, 1);
+            const float nx = math.update6(m.x, q.x, a.x, c.x, left, b.y);
+            const float nz = math.update6(m.z, q.z, a.z, c.z, b.y, b.w);
             if (active & 1u) nw.x = nx;
             if (active & 4u) nw.z = nz;
         } else {
-            float right = __shfl_down_sync(0xffffffffu, cur.x, 1);
-            if (lane == 31 && x2 + 4 < p.pitch) {
-                right = c[4];
-            }
-            const float ny = math.update6(a0.y, a1.y, b0v.y, b1v.y, cur.x, cur.z);
-            const float nq = math.update6(a0.w, a1.w, b0v.w, b1v.w, cur.z, right);
+            const float right = __shfl_down_sync(0xffffffffu, b.x, 1);
+            const float ny = math.update6(m.y, q.y, a.y, c.y, b.x, b.z);
+            const float nq = math.update6(m.w, q.w, a.w, c.w, b.z, right);
             if (active & 2u) nw.y = ny;
             if (active & 8u) nw.w = nq;
         }
-        if (active != 0u) {
-            if (p.check) {
-                float d = fabsf(__fsub_rn(cur.x, nw.x));
-                if (d > dmax) dmax = d;
-                d = fabsf(__fsub_rn(cur.y, nw.y));
-                if (d > dmax) dmax = d;
-                d = fabsf(__fsub_rn(cur.z, nw.z));
-                if (d > dmax) dmax = d;
-                d = fabsf(__fsub_rn(cur.w, nw.w));
-                if (d > dmax) dmax = d;
+        if (CHECK && chk) {
+            // |prev - new| is 0 for cells that were not updated
+            float d = fabsf(__fsub_rn(b.x, nw.x));
+            if (d > dmax) dmax = d;
+            d = fabsf(__fsub_rn(b.y, nw.y));
+            if (d > dmax) dmax = d;
+            d = fabsf(__fsub_rn(b.z, nw.z));
+            if (d > dmax) dmax = d;
+            d = fabsf(__fsub_rn(b.w, nw.w));
+            if (d > dmax) dmax = d;
+        }
+        *reinterpret_cast<float4 *>(pc + r * k3W + lane * 4) = nw;
+        b = nw;
+    }
+
+    // Rows [ra, rb) of one layer.  par = (it + x0 + x1 of tile row 0) & 1: cell (r, c) is active when
+    // (par + r + c) is even.  chk_lo / chk_hi: rows whose deltas count (the output rows), for lanes with chk.
+    template <bool CHECK>
+    __device__ __forceinline__ void band(float *pc, const float *pm, const float *pp, const uint8_t *mk, int ra, int rb,
+                                         uint32_t par, bool chk, int chk_lo, int chk_hi)
+    {
+        if (ra >= rb) {
+            return;
+        }
+        float4 a = ld(pc, ra - 1, lane), b = ld(pc, ra, lane), c;
+        int r = ra;
+        if (((par + (uint32_t)r) & 1u) != 0u) {   // first row has its odd columns active: peel it
+            c = ld(pc, r + 1, lane);
+            row<false, CHECK>(pc, pm, pp, mk, r, a, b, c, chk && r >= chk_lo && r < chk_hi);
+            a = b;
+            b = c;
+            ++r;
+        }
+        for (; r + 1 < rb; r += 2) {
+            c = ld(pc, r + 1, lane);
+            row<true, CHECK>(pc, pm, pp, mk, r, a, b, c, chk && r >= chk_lo && r < chk_hi);
+            a = ld(pc, r + 2, lane);
+            row<false, CHECK>(pc, pm, pp, mk, r + 1, b, c, a, chk && r + 1 >= chk_lo && r + 1 < chk_hi);
+            b = a;
+            a = c;
+        }
+        if (r < rb) {
+            c = ld(pc, r + 1, lane);
+            row<true, CHECK>(pc, pm, pp, mk, r, a, b, c, chk && r >= chk_lo && r < chk_hi);
+        }
+    }
+};
+
+template <class Math>
+__global__ void __launch_bounds__(k3Threads, 2)
+sweep3d_kernel(const __grid_constant__ CUtensorMap src_map, const Sweep3DParams p, const Math math_in)
+{
+    if (*p.ctrl_done) {
+        return;  // a previous check sweep already met the termination rule
+    }
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int BH = (int)p.BH;
+    const int plane_floats = BH * k3W;
+    float *planes = reinterpret_cast<float *>(smem_raw);
+    uint8_t *masks = smem_raw + (size_t)k3Slots * plane_floats * sizeof(float);
+    MathTables *tables = reinterpret_cast<MathTables *>(masks + (size_t)k3Slots * BH * k3G);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(tables + 1);
+    float *s_red = reinterpret_cast<float *>(bars + k3Slots);
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler (see sweep2d.cuh)
+    const uint32_t tiles_xy = p.ntx * p.nty;
+    const int tz = blockIdx.x / tiles_xy;
+    const int txy = blockIdx.x % tiles_xy;
+    const int tx = txy % p.ntx, ty = txy / p.ntx;
+    const int gx0 = tx * k3OutW - k3HC;                        // x2 of tile column 0
+    const int gy0 = ty * (BH - 2 * k3HR) - k3HR;               // x1 of tile row 0
+    const int z0 = (int)p.own_lo + tz * (int)p.zchunk;         // first output layer (buffer layer)
+    const int z1 = min(z0 + (int)p.zchunk, (int)p.own_hi);
+    const int L = z1 - z0 + 2 * k3HR;                          // layers this CTA touches: local j = 0 .. L-1
+    const int layer0 = z0 - k3HR;                              // buffer layer of j = 0
+
+    if (tid == 0) {
+        for (int i = 0; i < k3Slots; ++i) {
+            mbar_init(&bars[i], 1);
+        }
+    }
+    __syncthreads();
+
+    auto issue_load = [&](int j) {   // thread 0 only
+        const int slot = j % k3Slots;
+        mbar_expect_tx(&bars[slot], (uint32_t)(plane_floats * sizeof(float)));
+        tma_load_2d(planes + (size_t)slot * plane_floats, &src_map, gx0, (layer0 + j) * (int)p.m1 + gy0, &bars[slot]);
+    };
+    // may-update nibbles of layer j: one byte per float4 group, bit i = cell i of the group is free, inside
+    // the grid's interior, and has all six neighbours in the tile
+    auto build_mask = [&](int j) {
+        const int slot = j % k3Slots;
+        const int layer = layer0 + j;
+        const int64_t x0 = p.grow0 + layer;
+        const bool layer_ok = layer >= 0 && layer < (int)p.buf_layers && x0 > 0 && x0 < (int64_t)p.m0 - 1;
+        const int w0 = gx0 >> 5;        // floor division, gx0 may be negative
+        const int sh = gx0 - (w0 << 5);
+        for (int item = tid; item < BH * 4; item += k3Threads) {
+            const int r = item >> 2, w = item & 3;
+            const int x1 = gy0 + r;
+            uint32_t bits = 0;
+            if (layer_ok && r > 0 && r < BH - 1 && x1 > 0 && x1 < (int)p.m1 - 1) {
+                const uint32_t *row = p.freemask + ((size_t)layer * p.m1 + (size_t)x1) * p.mask_wpr;
+                const int wa = w0 + w, wb = wa + 1;
+                const uint32_t lo = (wa >= 0 && wa < (int)p.mask_wpr) ? __ldg(row + wa) : 0u;
+                const uint32_t hi = (wb >= 0 && wb < (int)p.mask_wpr) ? __ldg(row + wb) : 0u;
+                bits = __funnelshift_r(lo, hi, sh);
+                if (w == 0) bits &= ~1u;            // tile column 0: no left neighbour in the tile
+                if (w == 3) bits &= ~0x80000000u;   // tile column 127
+                const int x_first = gx0 + w * 32;   // x2 of bit 0
+                if (x_first <= 0 && x_first + 31 >= 0) bits &= ~(1u << (0 - x_first));
+                const int x_last = (int)p.m2 - 1;
+                if (x_first <= x_last && x_first + 31 >= x_last) bits &= ~(1u << (x_last - x_first));
             }
-            // Only the active colour's words are stored: the other colour's words in this float4 are
-            // being read by neighbouring warps and must not be rewritten with possibly stale copies
-            // (they are unchanged here, but a partial-word store keeps the sweep formally race-free).
-            if (active & 1u) c[0] = nw.x;
-            if (active & 2u) c[1] = nw.y;
-            if (active & 4u) c[2] = nw.z;
-            if (active & 8u) c[3] = nw.w;
-            float *q = nullptr;
-            if (p.peer_up != nullptr && b0 == p.own_lo) {
-                q = p.peer_up + (uint64_t)x1 * p.pitch + x2;
-            } else if (p.peer_down != nullptr && b0 + 1 == p.own_hi) {
-                q = p.peer_down + (uint64_t)x1 * p.pitch + x2;
+            uint2 packed;
+            packed.x = (bits & 0xFu) | ((bits & 0xF0u) << 4) | ((bits & 0xF00u) << 8) | ((bits & 0xF000u) << 12);
+            bits >>= 16;
+            packed.y = (bits & 0xFu) | ((bits & 0xF0u) << 4) | ((bits & 0xF00u) << 8) | ((bits & 0xF000u) << 12);
+            *reinterpret_cast<uint2 *>(masks + (size_t)slot * BH * k3G + r * k3G + w * 8) = packed;
+        }
+    };
+
+    const int first_loads = min(L, 4);
+    if (tid == 0) {
+        for (int j = 0; j < first_loads; ++j) {
+            issue_load(j);
+        }
+    }
+    load_math_tables(tables, tid, k3Threads);
+    for (int j = 0; j < first_loads; ++j) {
+        build_mask(j);
+    }
+    __syncthreads();
+
+    Math math = math_in;
+    math.bind(tables);
+    Rows3D<Math> rows{math, lane, 0.0f};
+
+    const int col = lane * 4;
+    const bool lane_out = col >= k3HC && col < k3W - k3HC;      // lanes 1 .. 30
+    const int perA = (BH - 2 + 7) / 8, perB = (BH - 2 * k3HR + 7) / 8;
+    const int raA = 1 + warp * perA, rbA = min(raA + perA, BH - 1);
+    const int raB = k3HR + warp * perB, rbB = min(raB + perB, BH - k3HR);
+    const bool two = p.count >= 2;
+    // colour parity of tile row 0, column 0 at iteration it0, layer j = 0 (gx0 is even)
+    const uint32_t par0 = (p.it0 + (uint32_t)(p.grow0 + layer0) + (uint32_t)gy0) & 1u;
+
+    auto slot_plane = [&](int j) { return planes + (size_t)(j % k3Slots) * plane_floats; };
+    auto slot_mask = [&](int j) { return masks + (size_t)(j % k3Slots) * BH * k3G; };
+    auto wait_layer = [&](int j) { mbar_wait(&bars[j % k3Slots], (uint32_t)((j / k3Slots) & 1)); };
+    auto owned = [&](int j) { return j >= k3HR && j < L - k3HR; };
+
+    // A warp stores whole rows of layer j's output region (lanes 1..30 hold its 120 columns).
+    auto write_back = [&](int j) {
+        const int layer = layer0 + j;
+        const float *pl = slot_plane(j);
+        float *up = nullptr, *dn = nullptr;
+        if (p.peer_up != nullptr && layer < (int)(p.own_lo + p.halo_layers)) {
+            up = p.peer_up + (size_t)(layer - (int)p.own_lo) * p.layer_floats;
+        }
+        if (p.peer_down != nullptr && layer >= (int)(p.own_hi - p.halo_layers)) {
+            dn = p.peer_down + (size_t)(layer - (int)(p.own_hi - p.halo_layers)) * p.layer_floats;
+        }
+        float *base = p.dst + (size_t)layer * p.layer_floats;
+        const int r_end = min(BH - k3HR, (int)p.m1 - gy0);
+        const bool lane_ok = lane_out && gx0 + col < (int)p.pitch;
+        for (int r = k3HR + warp; r < r_end; r += k3Threads / 32) {
+            if (lane_ok) {
+                const size_t off = (size_t)(gy0 + r) * p.pitch + (size_t)(gx0 + col);
+                const float4 v = *reinterpret_cast<const float4 *>(pl + r * k3W + col);
+                *reinterpret_cast<float4 *>(base + off) = v;
+                if (up != nullptr) {
+                    *reinterpret_cast<float4 *>(up + off) = v;
+                }
+                if (dn != nullptr) {
+                    *reinterpret_cast<float4 *>(dn + off) = v;
+                }
             }
-            if (q != nullptr) {
-                if (active & 1u) q[0] = nw.x;
-                if (active & 2u) q[1] = nw.y;
-                if (active & 4u) q[2] = nw.z;
-                if (active & 8u) q[3] = nw.w;
+        }
+    };
+
+    for (int s = 1; s <= L - 2; ++s) {
+        // every thread is past the barrier that ended step s-1: the slot of layer s-3 is free
+        if (s + 3 < L) {
+            if (tid == 0) {
+                fence_proxy_async_smem();
+                issue_load(s + 3);
             }
-            if (p.peer_up != nullptr && p.peer_down != nullptr && b0 == p.own_lo && b0 + 1 == p.own_hi) {
-                q = p.peer_down + (uint64_t)x1 * p.pitch + x2;   // a one-layer slab feeds both neighbours
-                if (active & 1u) q[0] = nw.x;
-                if (active & 2u) q[1] = nw.y;
-                if (active & 4u) q[2] = nw.z;
-                if (active & 8u) q[3] = nw.w;
+            build_mask(s + 3);
+        }
+        if (s == 1) {
+            wait_layer(0);
+            wait_layer(1);
+        }
+        wait_layer(s + 1);
+
+        // colour A on layer s
+        {
+            const uint32_t par = (par0 + (uint32_t)s) & 1u;
+            const bool chk = p.check && !two && lane_out && owned(s);
+            if (p.check && !two) {
+                rows.template band<true>(slot_plane(s), slot_plane(s - 1), slot_plane(s + 1), slot_mask(s), raA, rbA, par, chk,
+                                         k3HR, BH - k3HR);
+            } else {
+                rows.template band<false>(slot_plane(s), slot_plane(s - 1), slot_plane(s + 1), slot_mask(s), raA, rbA, par,
+                                          false, 0, 0);
             }
+        }
+        __syncthreads();
+        if (two) {
+            if (s >= 3) {
+                // colour B (iteration it0 + 1) on layer s-1
+                const uint32_t par = (par0 + 1u + (uint32_t)(s - 1)) & 1u;
+                const bool chk = p.check && lane_out && owned(s - 1);
+                if (p.check) {
+                    rows.template band<true>(slot_plane(s - 1), slot_plane(s - 2), slot_plane(s), slot_mask(s - 1), raB, rbB,
+                                             par, chk, k3HR, BH - k3HR);
+                } else {
+                    rows.template band<false>(slot_plane(s - 1), slot_plane(s - 2), slot_plane(s), slot_mask(s - 1), raB, rbB,
+                                              par, false, 0, 0);
+                }
+                __syncthreads();
+                if (owned(s - 1)) {
+                    write_back(s - 1);
+                }
+            }
+        } else if (owned(s)) {
+            write_back(s);
         }
     }
 
     if (p.check) {
+        float dmax = rows.dmax;
         for (int o = 16; o > 0; o >>= 1) {
             dmax = fmaxf(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
         }
@@ -165,7 +357,7 @@ sweep3d_kernel(const Sweep3DParams p, const Math math_in)
         __syncthreads();
         if (tid == 0) {
             float m = 0.0f;
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < k3Threads / 32; ++i) {
                 m = fmaxf(m, s_red[i]);
             }
             if (m > 0.0f) {

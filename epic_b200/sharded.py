@@ -43,7 +43,7 @@ class GpuSlab:
         dev = torch.cuda.current_device() if device is None else device
         stream = torch.cuda.current_stream(dev).cuda_stream
         # ghost depth = sweeps per pass; query T from a probe of the library defaults
-        probe_T = 4 if len(self.shape) == 2 else 1
+        probe_T = 4 if len(self.shape) == 2 else 2
         self.ghost = probe_T if world > 1 else 0
         self.field = Field(self.shape, self.row0, self.rows, self.ghost, math=math, device=dev, stream=stream)
         info = self.field.info()
