@@ -190,6 +190,19 @@ int Field::create(Field **out, unsigned n, const uint64_t *gm, uint64_t row0, ui
             return kInvalidCudaParam;
         }
         f->attr_done_ = true;
+        int k = 0;
+        const cudaError_t e = (cfg.math == MATH_STRICT)
+            ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k, sweep3d_kernel<StrictMath>, k3Threads, smem)
+            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k, sweep3d_kernel<FastMath>, k3Threads, smem);
+        if (e != cudaSuccess || k < 1) {
+            cudaGetLastError();
+            k = 1;
+        }
+        f->ctas_per_sm_ = k;
+        if (gm[1] * f->pitch_ >= 0x80000000ull) {
+            delete f;
+            return kInvalidData;   // the 3-D kernel addresses a layer with 32-bit offsets
+        }
     }
     if (n == 2) {
         // Tile geometry: estimate the time of one pass for every candidate (threads, tile rows) and keep
@@ -748,11 +761,11 @@ int Field::launch_pass_3d(uint32_t it0, uint32_t count, bool check_last)
     p.BH = (uint32_t)TH_;
     p.ntx = (uint32_t)((gm_[2] + k3OutW - 1) / k3OutW);
     p.nty = (uint32_t)((gm_[1] + (p.BH - 2 * k3HR) - 1) / (p.BH - 2 * k3HR));
-    // Layers per CTA: a CTA costs (its layers + the 2 * 2 halo layers); the grid runs in waves of two CTAs
-    // per SM.  Take the split along x0 with the cheapest estimated pass.
+    // Layers per CTA: a CTA costs (its layers + the 2 * 2 halo layers); the grid runs in waves of
+    // ctas_per_sm_ CTAs per SM.  Take the split along x0 with the cheapest estimated pass.
     {
         const uint64_t tiles_xy = (uint64_t)p.ntx * p.nty;
-        const uint64_t slots = 2ull * (uint64_t)sms_;
+        const uint64_t slots = (uint64_t)ctas_per_sm_ * (uint64_t)sms_;
         uint64_t best_cost = 0;
         uint32_t best_chunk = (uint32_t)rows_;
         const uint64_t max_ntz = std::max<uint64_t>(1, std::min<uint64_t>(256, rows_ / 4));

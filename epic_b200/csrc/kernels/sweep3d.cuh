@@ -13,11 +13,11 @@
 // TMA unit as a 2-D tensor of pitch x (layers * m1), so rows outside the grid come from the
 // neighbouring layer or are zero-filled; they only ever feed cells whose results are masked).  At
 // step s the CTA
-//     sweeps colour A (iteration it0) on layer s       -- reads layers s-1, s, s+1,
-//     sweeps colour B (iteration it0 + 1) on layer s-1 -- reads layers s-2, s-1, s, all of which have
-//                                                         had their colour-A sweep,
+//     sweeps colour A (iteration it0) on layer s+1     -- reads layers s, s+1, s+2,
+//     sweeps colour B (iteration it0 + 1) on layer s-1 -- reads layers s-2, s-1, s, all of which had their
+//                                                         colour-A sweep in an earlier step,
 //     writes layer s-1 (now two iterations ahead) to the destination buffer, and
-//     has the loads of layers s+2 and s+3 in flight.
+//     has the load of layer s+3 in flight (and layer s+5 on its way into L2).
 // DRAM sees every cell once for reading (plus the halo overlap) and once for writing per TWO
 // half-sweeps; the per-launch work is the same arithmetic as the 2-D kernel with two more
 // neighbours.  With count == 1 only the colour-A sweep runs and layer s is written.
@@ -82,9 +82,16 @@ struct Rows3D {
     int lane;
     float dmax;
 
+    // One LDS.128 per lane (conflict-free across the warp).  Written in PTX because the compiler otherwise
+    // narrows a float4 load of which only two components are used into two LDS.32 with a 16-byte lane stride
+    // -- four-way bank conflicts on each (profiles/r01d_sweep3d_fast_ncu.md).
     static __device__ __forceinline__ float4 ld(const float *plane, int r, int lane)
     {
-        return *reinterpret_cast<const float4 *>(plane + r * k3W + lane * 4);
+        float4 v;
+        asm volatile("ld.volatile.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                     : "r"(smem_u32(plane + r * k3W + lane * 4)));
+        return v;
     }
 
     // One tile row: `b` = this row (updated in place), a / c = rows r-1 / r+1 of the same layer,
@@ -204,37 +211,43 @@ sweep3d_kernel(const __grid_constant__ CUtensorMap src_map, const Sweep3DParams 
         tma_load_2d(planes + (size_t)slot * plane_floats, &src_map, gx0, (layer0 + j) * (int)p.m1 + gy0, &bars[slot]);
     };
     // may-update nibbles of layer j: one byte per float4 group, bit i = cell i of the group is free, inside
-    // the grid's interior, and has all six neighbours in the tile
-    auto build_mask = [&](int j) {
-        const int slot = j % k3Slots;
+    // the grid's interior, and has all six neighbours in the tile.  One item (row, 32-column word) per thread;
+    // mask_fetch issues the global loads, mask_commit (after the step's arithmetic, so that the load latency
+    // is hidden) packs them into shared memory.
+    const int w0 = gx0 >> 5;        // floor division, gx0 may be negative
+    const int sh = gx0 - (w0 << 5);
+    const int mrow = tid >> 2, mword = tid & 3;
+    const bool mitem = tid < BH * 4;
+    auto mask_fetch = [&](int j, uint32_t &lo, uint32_t &hi) {
         const int layer = layer0 + j;
         const int64_t x0 = p.grow0 + layer;
-        const bool layer_ok = layer >= 0 && layer < (int)p.buf_layers && x0 > 0 && x0 < (int64_t)p.m0 - 1;
-        const int w0 = gx0 >> 5;        // floor division, gx0 may be negative
-        const int sh = gx0 - (w0 << 5);
-        for (int item = tid; item < BH * 4; item += k3Threads) {
-            const int r = item >> 2, w = item & 3;
-            const int x1 = gy0 + r;
-            uint32_t bits = 0;
-            if (layer_ok && r > 0 && r < BH - 1 && x1 > 0 && x1 < (int)p.m1 - 1) {
-                const uint32_t *row = p.freemask + ((size_t)layer * p.m1 + (size_t)x1) * p.mask_wpr;
-                const int wa = w0 + w, wb = wa + 1;
-                const uint32_t lo = (wa >= 0 && wa < (int)p.mask_wpr) ? __ldg(row + wa) : 0u;
-                const uint32_t hi = (wb >= 0 && wb < (int)p.mask_wpr) ? __ldg(row + wb) : 0u;
-                bits = __funnelshift_r(lo, hi, sh);
-                if (w == 0) bits &= ~1u;            // tile column 0: no left neighbour in the tile
-                if (w == 3) bits &= ~0x80000000u;   // tile column 127
-                const int x_first = gx0 + w * 32;   // x2 of bit 0
-                if (x_first <= 0 && x_first + 31 >= 0) bits &= ~(1u << (0 - x_first));
-                const int x_last = (int)p.m2 - 1;
-                if (x_first <= x_last && x_first + 31 >= x_last) bits &= ~(1u << (x_last - x_first));
-            }
-            uint2 packed;
-            packed.x = (bits & 0xFu) | ((bits & 0xF0u) << 4) | ((bits & 0xF00u) << 8) | ((bits & 0xF000u) << 12);
-            bits >>= 16;
-            packed.y = (bits & 0xFu) | ((bits & 0xF0u) << 4) | ((bits & 0xF00u) << 8) | ((bits & 0xF000u) << 12);
-            *reinterpret_cast<uint2 *>(masks + (size_t)slot * BH * k3G + r * k3G + w * 8) = packed;
+        const int x1 = gy0 + mrow;
+        lo = 0u;
+        hi = 0u;
+        if (mitem && layer >= 0 && layer < (int)p.buf_layers && x0 > 0 && x0 < (int64_t)p.m0 - 1 && mrow > 0 &&
+            mrow < BH - 1 && x1 > 0 && x1 < (int)p.m1 - 1) {
+            const uint32_t *row = p.freemask + ((size_t)layer * p.m1 + (size_t)x1) * p.mask_wpr;
+            const int wa = w0 + mword, wb = wa + 1;
+            lo = (wa >= 0 && wa < (int)p.mask_wpr) ? __ldg(row + wa) : 0u;
+            hi = (wb >= 0 && wb < (int)p.mask_wpr) ? __ldg(row + wb) : 0u;
         }
+    };
+    auto mask_commit = [&](int j, uint32_t lo, uint32_t hi) {
+        if (!mitem) {
+            return;
+        }
+        uint32_t bits = __funnelshift_r(lo, hi, sh);
+        if (mword == 0) bits &= ~1u;            // tile column 0: no left neighbour in the tile
+        if (mword == 3) bits &= ~0x80000000u;   // tile column 127
+        const int x_first = gx0 + mword * 32;   // x2 of bit 0
+        if (x_first <= 0 && x_first + 31 >= 0) bits &= ~(1u << (0 - x_first));
+        const int x_last = (int)p.m2 - 1;       // the global border columns are never updated
+        if (x_first <= x_last && x_first + 31 >= x_last) bits &= ~(1u << (x_last - x_first));
+        uint2 packed;
+        packed.x = (bits & 0xFu) | ((bits & 0xF0u) << 4) | ((bits & 0xF00u) << 8) | ((bits & 0xF000u) << 12);
+        bits >>= 16;
+        packed.y = (bits & 0xFu) | ((bits & 0xF0u) << 4) | ((bits & 0xF00u) << 8) | ((bits & 0xF000u) << 12);
+        *reinterpret_cast<uint2 *>(masks + (size_t)(j % k3Slots) * BH * k3G + mrow * k3G + mword * 8) = packed;
     };
 
     const int first_loads = min(L, 4);
@@ -245,7 +258,9 @@ sweep3d_kernel(const __grid_constant__ CUtensorMap src_map, const Sweep3DParams 
     }
     load_math_tables(tables, tid, k3Threads);
     for (int j = 0; j < first_loads; ++j) {
-        build_mask(j);
+        uint32_t lo, hi;
+        mask_fetch(j, lo, hi);
+        mask_commit(j, lo, hi);
     }
     __syncthreads();
 
@@ -271,78 +286,92 @@ sweep3d_kernel(const __grid_constant__ CUtensorMap src_map, const Sweep3DParams 
     auto write_back = [&](int j) {
         const int layer = layer0 + j;
         const float *pl = slot_plane(j);
-        float *up = nullptr, *dn = nullptr;
+        const float *up = nullptr, *dn = nullptr;   // non-null: this layer also goes to that neighbour
         if (p.peer_up != nullptr && layer < (int)(p.own_lo + p.halo_layers)) {
-            up = p.peer_up + (size_t)(layer - (int)p.own_lo) * p.layer_floats;
+            up = p.peer_up;
         }
         if (p.peer_down != nullptr && layer >= (int)(p.own_hi - p.halo_layers)) {
-            dn = p.peer_down + (size_t)(layer - (int)(p.own_hi - p.halo_layers)) * p.layer_floats;
+            dn = p.peer_down;
         }
-        float *base = p.dst + (size_t)layer * p.layer_floats;
         const int r_end = min(BH - k3HR, (int)p.m1 - gy0);
-        const bool lane_ok = lane_out && gx0 + col < (int)p.pitch;
+        if (!(lane_out && gx0 + col < (int)p.pitch)) {
+            return;
+        }
+        // 32-bit offsets inside the layer (Field::create rejects layers of 2^31 floats or more)
+        uint32_t off = (uint32_t)(gy0 + k3HR + warp) * (uint32_t)p.pitch + (uint32_t)(gx0 + col);
+        const uint32_t step = (uint32_t)(k3Threads / 32) * (uint32_t)p.pitch;
+        const float *src = pl + (k3HR + warp) * k3W + col;
+        float *lay = p.dst + (size_t)layer * p.layer_floats;
+        float *lay_up = up ? p.peer_up + (size_t)(layer - (int)p.own_lo) * p.layer_floats : nullptr;
+        float *lay_dn = dn ? p.peer_down + (size_t)(layer - (int)(p.own_hi - p.halo_layers)) * p.layer_floats : nullptr;
         for (int r = k3HR + warp; r < r_end; r += k3Threads / 32) {
-            if (lane_ok) {
-                const size_t off = (size_t)(gy0 + r) * p.pitch + (size_t)(gx0 + col);
-                const float4 v = *reinterpret_cast<const float4 *>(pl + r * k3W + col);
-                *reinterpret_cast<float4 *>(base + off) = v;
-                if (up != nullptr) {
-                    *reinterpret_cast<float4 *>(up + off) = v;
-                }
-                if (dn != nullptr) {
-                    *reinterpret_cast<float4 *>(dn + off) = v;
-                }
+            const float4 v = *reinterpret_cast<const float4 *>(src);
+            *reinterpret_cast<float4 *>(lay + off) = v;
+            if (lay_up != nullptr) {
+                *reinterpret_cast<float4 *>(lay_up + off) = v;
             }
+            if (lay_dn != nullptr) {
+                *reinterpret_cast<float4 *>(lay_dn + off) = v;
+            }
+            off += step;
+            src += (k3Threads / 32) * k3W;
         }
     };
 
-    for (int s = 1; s <= L - 2; ++s) {
+    for (int s = 0; s <= L - 2; ++s) {
+        uint32_t mlo = 0u, mhi = 0u;
         // every thread is past the barrier that ended step s-1: the slot of layer s-3 is free
-        if (s + 3 < L) {
+        if (s >= 1 && s + 3 < L) {
             if (tid == 0) {
                 fence_proxy_async_smem();
                 issue_load(s + 3);
+                if (s + 5 < L) {   // warm L2 two layers further ahead
+                    tma_prefetch_2d(&src_map, gx0, (layer0 + s + 5) * (int)p.m1 + gy0);
+                }
             }
-            build_mask(s + 3);
+            mask_fetch(s + 3, mlo, mhi);
         }
-        if (s == 1) {
+        if (s == 0) {
             wait_layer(0);
             wait_layer(1);
         }
-        wait_layer(s + 1);
-
-        // colour A on layer s
-        {
-            const uint32_t par = (par0 + (uint32_t)s) & 1u;
-            const bool chk = p.check && !two && lane_out && owned(s);
+        if (s + 2 < L) {
+            wait_layer(s + 2);
+        }
+        if (s + 1 <= L - 2) {
+            // colour A (iteration it0) on layer s+1
+            const int j = s + 1;
+            const uint32_t par = (par0 + (uint32_t)j) & 1u;
             if (p.check && !two) {
-                rows.template band<true>(slot_plane(s), slot_plane(s - 1), slot_plane(s + 1), slot_mask(s), raA, rbA, par, chk,
-                                         k3HR, BH - k3HR);
+                rows.template band<true>(slot_plane(j), slot_plane(j - 1), slot_plane(j + 1), slot_mask(j), raA, rbA, par,
+                                         lane_out && owned(j), k3HR, BH - k3HR);
             } else {
-                rows.template band<false>(slot_plane(s), slot_plane(s - 1), slot_plane(s + 1), slot_mask(s), raA, rbA, par,
+                rows.template band<false>(slot_plane(j), slot_plane(j - 1), slot_plane(j + 1), slot_mask(j), raA, rbA, par,
                                           false, 0, 0);
             }
+        }
+        if (two && s >= 3) {
+            // colour B (iteration it0 + 1) on layer s-1
+            const int j = s - 1;
+            const uint32_t par = (par0 + 1u + (uint32_t)j) & 1u;
+            if (p.check) {
+                rows.template band<true>(slot_plane(j), slot_plane(j - 1), slot_plane(j + 1), slot_mask(j), raB, rbB, par,
+                                         lane_out && owned(j), k3HR, BH - k3HR);
+            } else {
+                rows.template band<false>(slot_plane(j), slot_plane(j - 1), slot_plane(j + 1), slot_mask(j), raB, rbB, par,
+                                          false, 0, 0);
+            }
+        }
+        if (s >= 1 && s + 3 < L) {
+            mask_commit(s + 3, mlo, mhi);   // its slot (layer s-3's) has been idle since step s-2
         }
         __syncthreads();
         if (two) {
             if (s >= 3) {
-                // colour B (iteration it0 + 1) on layer s-1
-                const uint32_t par = (par0 + 1u + (uint32_t)(s - 1)) & 1u;
-                const bool chk = p.check && lane_out && owned(s - 1);
-                if (p.check) {
-                    rows.template band<true>(slot_plane(s - 1), slot_plane(s - 2), slot_plane(s), slot_mask(s - 1), raB, rbB,
-                                             par, chk, k3HR, BH - k3HR);
-                } else {
-                    rows.template band<false>(slot_plane(s - 1), slot_plane(s - 2), slot_plane(s), slot_mask(s - 1), raB, rbB,
-                                              par, false, 0, 0);
-                }
-                __syncthreads();
-                if (owned(s - 1)) {
-                    write_back(s - 1);
-                }
+                write_back(s - 1);   // layers 2 .. L-3: exactly the owned ones
             }
-        } else if (owned(s)) {
-            write_back(s);
+        } else if (s + 1 <= L - 2 && owned(s + 1)) {
+            write_back(s + 1);
         }
     }
 
