@@ -328,6 +328,9 @@ Field::~Field()
             if (u_[i]) cudaFree(u_[i]);
         }
         close_peers();
+        for (PeriodGraph &g : graphs_) {
+            if (g.exec) cudaGraphExecDestroy(g.exec);
+        }
         if (freemask_) cudaFree(freemask_);
         if (flags_) cudaFree(flags_);
         if (ctrl_) cudaFree(ctrl_);
@@ -840,6 +843,73 @@ int Field::run(uint32_t it0, uint32_t count, bool check_last)
     return kSuccess;
 }
 
+int Field::run_period(uint32_t it0, uint32_t count)
+{
+    // Peer-to-peer halos order passes between GPUs with stream memory operations, and the legacy default
+    // stream cannot be captured: those cases launch directly.
+    const bool direct = graphs_off_ || has_peers() || stream_ == nullptr || stream_ == cudaStreamLegacy ||
+                        stream_ == cudaStreamPerThread || count < 2u * (uint32_t)T_;
+    if (!direct) {
+        const uint32_t key = ((uint32_t)cur_ << 1) | (it0 & 1u);
+        PeriodGraph &g = graphs_[key];
+        if (g.exec != nullptr && g.count != count) {
+            cudaGraphExecDestroy(g.exec);
+            g.exec = nullptr;
+        }
+        if (g.exec == nullptr) {
+            const int cur_before = cur_;
+            const uint64_t launches_before = launches_;
+            const uint32_t passes_before = pass_count_;
+            cudaGraph_t graph = nullptr;
+            bool ok = cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+            if (ok) {
+                ok = run(it0, count, true) == kSuccess;
+                decide_period_kernel<<<1, 1, 0, stream_>>>(ctrl_, count, (uint32_t)cur_);
+                launches_++;
+                ok = (cudaStreamEndCapture(stream_, &graph) == cudaSuccess) && ok && graph != nullptr;
+            }
+            if (ok) {
+                ok = cudaGraphInstantiate(&g.exec, graph, 0) == cudaSuccess;
+            }
+            if (graph != nullptr) {
+                cudaGraphDestroy(graph);
+            }
+            if (ok) {
+                g.key = key;
+                g.count = count;
+                g.cur_after = cur_;
+                g.launches = launches_ - launches_before;
+                g.passes = pass_count_ - passes_before;
+            } else {
+                cudaGetLastError();
+                g.exec = nullptr;
+                graphs_off_ = true;   // this driver / stream cannot capture: launch directly from now on
+            }
+            // nothing has run yet: rewind the host-side bookkeeping the capture advanced
+            cur_ = cur_before;
+            launches_ = launches_before;
+            pass_count_ = passes_before;
+        }
+        if (g.exec != nullptr) {
+            if (cudaGraphLaunch(g.exec, stream_) != cudaSuccess) {
+                cudaGetLastError();
+                return kKernelExecution;
+            }
+            cur_ = g.cur_after;
+            launches_ += g.launches;
+            pass_count_ += g.passes;
+            return kSuccess;
+        }
+    }
+    const int r = run(it0, count, true);
+    if (r != kSuccess) {
+        return r;
+    }
+    decide_period_kernel<<<1, 1, 0, stream_>>>(ctrl_, count, (uint32_t)cur_);
+    launches_++;
+    return cudaGetLastError() == cudaSuccess ? kSuccess : kKernelExecution;
+}
+
 int Field::read_delta(float *delta)
 {
     DeviceGuard guard(cfg_.device);
@@ -870,6 +940,8 @@ int Field::solve(float epsilon, uint32_t stagger, uint32_t m_max, uint32_t *iter
         cudaGetLastError();
         return kMemcpyToDevice;
     }
+    set_rule_kernel<<<1, 1, 0, stream_>>>(ctrl_, epsilon, m_max);
+    launches_++;
     // Period 0 is the check sweep at iteration 0; period k >= 1 covers iterations
     // (k-1)*stagger+1 .. k*stagger and ends with the check sweep at k*stagger
     // (reference harmonic_gpu.cu:266-282).  Two periods are kept in flight.
@@ -891,17 +963,22 @@ int Field::solve(float epsilon, uint32_t stagger, uint32_t m_max, uint32_t *iter
         if (it + count > 0xffffffffull) {
             return kInvalidData;  // the reference's 32-bit iteration counter would wrap
         }
-        int r = run((uint32_t)it, count, true);
+        int r;
+        if (period == 0) {
+            r = run((uint32_t)it, count, true);
+            if (r == kSuccess) {
+                decide_kernel<<<1, 1, 0, stream_>>>(ctrl_, epsilon, (uint32_t)(it + count), m_max, (uint32_t)cur_);
+                launches_++;
+                r = cudaGetLastError() == cudaSuccess ? kSuccess : kKernelExecution;
+            }
+        } else {
+            r = run_period((uint32_t)it, count);
+        }
         if (r != kSuccess) {
             return r;
         }
         it += count;
         const int slot = (int)(period % kSlots);
-        decide_kernel<<<1, 1, 0, stream_>>>(ctrl_, epsilon, (uint32_t)it, m_max, (uint32_t)cur_);
-        launches_++;
-        if (cudaGetLastError() != cudaSuccess) {
-            return kKernelExecution;
-        }
         if (cudaMemcpyAsync(&ctrl_host_[slot], ctrl_, sizeof(Ctrl), cudaMemcpyDeviceToHost, stream_) != cudaSuccess ||
             cudaEventRecord(events_[slot], stream_) != cudaSuccess) {
             cudaGetLastError();

@@ -133,6 +133,19 @@ private:
     int launch_pass(uint32_t it0, uint32_t count, bool check_last);
     int launch_pass_2d(uint32_t it0, uint32_t count, bool check_last);
     int launch_pass_3d(uint32_t it0, uint32_t count, bool check_last);
+    // One solver period (`count` half-sweeps ending in a check sweep, then the termination decision) as a
+    // CUDA graph: captured once per (starting buffer, colour phase, count) and replayed, so a period costs one
+    // launch call instead of count / T + 1 -- the small maps are bound by the host's launch rate otherwise.
+    int run_period(uint32_t it0, uint32_t count);
+    struct PeriodGraph {
+        uint32_t key = 0, count = 0;
+        cudaGraphExec_t exec = nullptr;
+        int cur_after = 0;
+        uint64_t launches = 0;
+        uint32_t passes = 0;
+    };
+    PeriodGraph graphs_[4];
+    bool graphs_off_ = false;
 
     FieldConfig cfg_;
     unsigned n_ = 0;

@@ -26,7 +26,10 @@ struct Ctrl {                      // device-resident control block
     float last_delta;              // delta of the most recent check sweep
     uint32_t last_check_iteration; // currentIteration right after that sweep
     uint32_t checks;               // number of check sweeps decided so far
-    uint32_t pad;
+    uint32_t iteration;            // currentIteration as the device sees it (replayed solver periods advance it)
+    float epsilon;                 // termination rule of the solve in progress: delta < epsilon ...
+    uint32_t m_max;                // ... and currentIteration >= m_max
+    uint32_t pad[2];
 };
 
 // One warp packs 32 consecutive cells of one row into one mask word (ballot), coalesced reads.
@@ -110,8 +113,38 @@ __global__ void decide_kernel(Ctrl *ctrl, float epsilon, uint32_t it_after, uint
     ctrl->delta_bits = 0u;
     ctrl->last_delta = delta;
     ctrl->last_check_iteration = it_after;
+    ctrl->iteration = it_after;
     ctrl->checks += 1u;
     if (delta < epsilon && it_after >= m_max) {
+        ctrl->final_iteration = it_after;
+        ctrl->final_buffer = buffer;
+        __threadfence();
+        ctrl->done = 1u;
+    }
+}
+
+// The same decision for a solver period replayed from a CUDA graph: nothing that changes from period to
+// period may be a kernel argument, so the iteration counter and the rule's constants live in `ctrl`
+// (set_rule_kernel).  `count` = half-sweeps of the period, `buffer` = the ping-pong buffer it ends in.
+__global__ void set_rule_kernel(Ctrl *ctrl, float epsilon, uint32_t m_max)
+{
+    ctrl->epsilon = epsilon;
+    ctrl->m_max = m_max;
+}
+
+__global__ void decide_period_kernel(Ctrl *ctrl, uint32_t count, uint32_t buffer)
+{
+    if (ctrl->done) {
+        return;
+    }
+    const float delta = __uint_as_float(ctrl->delta_bits);
+    const uint32_t it_after = ctrl->iteration + count;
+    ctrl->delta_bits = 0u;
+    ctrl->last_delta = delta;
+    ctrl->last_check_iteration = it_after;
+    ctrl->iteration = it_after;
+    ctrl->checks += 1u;
+    if (delta < ctrl->epsilon && it_after >= ctrl->m_max) {
         ctrl->final_iteration = it_after;
         ctrl->final_buffer = buffer;
         __threadfence();
