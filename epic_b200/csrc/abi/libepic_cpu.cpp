@@ -307,6 +307,52 @@ int harmonic_utilities_set_cells_2d_cpu(Harmonic *harmonic, unsigned int k, unsi
     return EPIC_SUCCESS;
 }
 
+// ---- extensions: dense map ingest (what the node's /map handler and reset-free-cells service compute
+// before they call set_cells: src/epic_navigation_node_harmonic.cpp:383-426, :582-611) ---------------------
+
+int harmonic_utilities_set_occupancy_grid_2d_cpu(Harmonic *harmonic, const signed char *data, int obstacleThreshold,
+                                                 int noChangeValue)
+{
+    const char *fn = "harmonic_utilities_set_occupancy_grid_2d_cpu";
+    if (harmonic == nullptr || harmonic->n != 2 || harmonic->m == nullptr || harmonic->u == nullptr ||
+        harmonic->locked == nullptr || data == nullptr) {
+        complain(fn, "Invalid data.");
+        return EPIC_ERROR_INVALID_DATA;
+    }
+    const unsigned int h = harmonic->m[0], w = harmonic->m[1];
+    for (unsigned int y = 1; y + 1 < h; y++) {
+        for (unsigned int x = 1; x + 1 < w; x++) {
+            const size_t c = (size_t)y * w + x;
+            const bool goal = harmonic->u[c] == (float)EPIC_LOG_SPACE_GOAL && harmonic->locked[c] == 1;
+            if (data[c] == noChangeValue || goal) {
+                continue;
+            }
+            const bool obstacle = data[c] >= obstacleThreshold;
+            harmonic->u[c] = obstacle ? (float)EPIC_LOG_SPACE_OBSTACLE : (float)EPIC_LOG_SPACE_FREE;
+            harmonic->locked[c] = obstacle ? 1 : 0;
+        }
+    }
+    return EPIC_SUCCESS;
+}
+
+int harmonic_utilities_reset_free_cells_2d_cpu(Harmonic *harmonic)
+{
+    if (harmonic == nullptr || harmonic->n != 2 || harmonic->m == nullptr || harmonic->u == nullptr ||
+        harmonic->locked == nullptr) {
+        complain("harmonic_utilities_reset_free_cells_2d_cpu", "Invalid data.");
+        return EPIC_ERROR_INVALID_DATA;
+    }
+    const unsigned int h = harmonic->m[0], w = harmonic->m[1];
+    for (unsigned int y = 1; y + 1 < h; y++) {
+        for (unsigned int x = 1; x + 1 < w; x++) {
+            if (harmonic->locked[(size_t)y * w + x] == 0) {
+                harmonic->u[(size_t)y * w + x] = (float)EPIC_LOG_SPACE_FREE;
+            }
+        }
+    }
+    return EPIC_SUCCESS;
+}
+
 // ---- harmonic_path_cpu.cpp:41-232 -----------------------------------------------------------------------
 
 static bool host_grid(const Harmonic *h, GridView<float> &g)

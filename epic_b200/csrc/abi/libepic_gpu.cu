@@ -561,6 +561,53 @@ int harmonic_utilities_set_cells_2d_gpu(Harmonic *harmonic, unsigned int numThre
     return r;
 }
 
+// ---- extensions: dense map ingest on the device-resident field ----------------------------------------
+
+int harmonic_utilities_set_occupancy_grid_2d_gpu(Harmonic *harmonic, const signed char *data, int obstacleThreshold,
+                                                 int noChangeValue)
+{
+    const char *fn = "harmonic_utilities_set_occupancy_grid_2d_gpu";
+    if (harmonic == nullptr || harmonic->n == 0 || harmonic->m == nullptr || data == nullptr) {
+        complain(fn, "Invalid data.");
+        return EPIC_ERROR_INVALID_DATA;
+    }
+    Context *c = resident(harmonic);
+    if (c == nullptr || c->n != 2) {
+        complain(fn, "Invalid data.");
+        return EPIC_ERROR_INVALID_DATA;
+    }
+    int r = issue_queued(c, true);
+    if (r == EPIC_SUCCESS) {
+        r = c->field->ingest_occupancy_2d(data, 0, c->m[0], obstacleThreshold, noChangeValue);
+    }
+    if (r != EPIC_SUCCESS) {
+        complain(fn, "Failed to classify the occupancy grid on the device.");
+    }
+    return r;
+}
+
+int harmonic_utilities_reset_free_cells_2d_gpu(Harmonic *harmonic)
+{
+    const char *fn = "harmonic_utilities_reset_free_cells_2d_gpu";
+    if (harmonic == nullptr || harmonic->n == 0 || harmonic->m == nullptr) {
+        complain(fn, "Invalid data.");
+        return EPIC_ERROR_INVALID_DATA;
+    }
+    Context *c = resident(harmonic);
+    if (c == nullptr || c->n != 2) {
+        complain(fn, "Invalid data.");
+        return EPIC_ERROR_INVALID_DATA;
+    }
+    int r = issue_queued(c, true);
+    if (r == EPIC_SUCCESS) {
+        r = c->field->reset_free_cells_2d();
+    }
+    if (r != EPIC_SUCCESS) {
+        complain(fn, "Failed to reset the free cells on the device.");
+    }
+    return r;
+}
+
 // ---- extensions: streamlines on the device-resident field -------------------------------------------
 
 int harmonic_compute_potential_2d_gpu(Harmonic *harmonic, float x, float y, float &potential)

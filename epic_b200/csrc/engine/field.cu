@@ -1055,6 +1055,71 @@ int Field::set_cells_2d(uint32_t k, const uint32_t *v, const uint32_t *types)
     return kSuccess;
 }
 
+int Field::ingest_occupancy_2d(const signed char *host, uint64_t first, uint64_t layers, int threshold, int no_change)
+{
+    if (n_ != 2 || host == nullptr || !range_ok(grow0_, buf_layers_, first, layers)) {
+        return kInvalidData;
+    }
+    DeviceGuard guard(cfg_.device);
+    if (wait_peers() != kSuccess) {
+        return kDeviceSynchronize;
+    }
+    const uint64_t m1 = gm_[1];
+    const uint64_t chunk_rows = std::max<uint64_t>(1, std::min<uint64_t>(layers, (64ull << 20) / m1));
+    int r = ensure_staging(&staging_, &staging_bytes_, chunk_rows * m1);
+    if (r != kSuccess) {
+        return r;
+    }
+    const uint32_t words = (uint32_t)((m1 + 31) / 32);
+    for (uint64_t done = 0; done < layers; done += chunk_rows) {
+        const uint64_t nrows = std::min(chunk_rows, layers - done);
+        if (cudaMemcpyAsync(staging_, host + done * m1, nrows * m1, cudaMemcpyHostToDevice, stream_) != cudaSuccess) {
+            cudaGetLastError();
+            return kMemcpyToDevice;
+        }
+        const uint64_t b0 = (uint64_t)((int64_t)(first + done) - grow0_);
+        const uint64_t threads = nrows * words * 32;
+        reclassify_2d_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream_>>>(
+            u_[cur_] + b0 * pitch_, freemask_ + b0 * mask_wpr_, pitch_, (uint32_t)mask_wpr_, (uint32_t)gm_[0], (uint32_t)m1,
+            (int64_t)(first + done), (uint32_t)nrows, (const signed char *)staging_, (int64_t)(first + done), threshold,
+            no_change, 0);
+        launches_++;
+        if (cudaGetLastError() != cudaSuccess) {
+            return kKernelExecution;
+        }
+        if (cudaStreamSynchronize(stream_) != cudaSuccess) {   // the staging buffer is reused
+            cudaGetLastError();
+            return kDeviceSynchronize;
+        }
+    }
+    return kSuccess;
+}
+
+int Field::reset_free_cells_2d()
+{
+    if (n_ != 2) {
+        return kInvalidData;
+    }
+    DeviceGuard guard(cfg_.device);
+    if (wait_peers() != kSuccess) {
+        return kDeviceSynchronize;
+    }
+    const uint32_t words = (uint32_t)((gm_[1] + 31) / 32);
+    const uint64_t threads = buf_layers_ * words * 32;
+    reclassify_2d_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream_>>>(
+        u_[cur_], freemask_, pitch_, (uint32_t)mask_wpr_, (uint32_t)gm_[0], (uint32_t)gm_[1], grow0_, (uint32_t)buf_layers_,
+        nullptr, 0, 0, 0, 1);
+    launches_++;
+    if (cudaGetLastError() != cudaSuccess) {
+        return kKernelExecution;
+    }
+    if (cudaStreamSynchronize(stream_) != cudaSuccess) {
+        cudaGetLastError();
+        return kDeviceSynchronize;
+    }
+    return kSuccess;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Streamlines
 

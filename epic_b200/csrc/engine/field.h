@@ -80,6 +80,11 @@ public:
     // k sparse edits (x = column, y = global row), types 0 goal / 1 obstacle / 2 free.
     int set_cells_2d(uint32_t k, const uint32_t *v, const uint32_t *types);
 
+    // Dense map ingest (2-D): an occupancy grid of one byte per cell covering global rows
+    // [first, first + layers), classified on the device; and "reset free cells".  See reclassify_2d_kernel.
+    int ingest_occupancy_2d(const signed char *host, uint64_t first, uint64_t layers, int threshold, int no_change);
+    int reset_free_cells_2d();
+
     // Streamlines on the device-resident field (2-D fields holding the rows the path visits).
     // Same arithmetic, operation for operation, as the reference's CPU functions.
     int potential_2d(float x, float y, float *value);

@@ -102,6 +102,57 @@ __global__ void set_cells_2d_kernel(float *__restrict__ u, uint32_t *__restrict_
     }
 }
 
+// Dense reclassification of the interior cells, one warp per mask word (32 cells of a row).  Replaces the
+// k = N scatter lists the reference's node builds for every /map message and for reset-free-cells
+// (src/epic_navigation_node_harmonic.cpp:383-426, :582-611; 12 bytes per cell over PCIe, one thread per
+// edit) with one byte per cell (mode 0) or nothing at all (mode 1):
+//   mode 0  occupancy grid: cells whose value is `no_change` and goal cells (locked with u == 0, the
+//           node's isCellGoal) keep their state; value >= threshold -> obstacle (u = -1e6, locked);
+//           anything else -> free (u = -1e6, unlocked) -- harmonic_utilities_set_cells_2d's type table.
+//   mode 1  every unlocked interior cell back to u = -1e6.
+// `occ` is dense over the rows this slab holds: occ[(row - occ_row0) * m1 + x].
+__global__ void reclassify_2d_kernel(float *__restrict__ u, uint32_t *__restrict__ mask, uint64_t pitch,
+                                     uint32_t mask_wpr, uint32_t m0, uint32_t m1, int64_t grow0, uint32_t buf_rows,
+                                     const signed char *__restrict__ occ, int64_t occ_row0, int threshold,
+                                     int no_change, int mode)
+{
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t words = (m1 + 31u) / 32u;
+    if (warp >= (uint64_t)buf_rows * words) {
+        return;
+    }
+    const uint32_t b = (uint32_t)(warp / words), w = (uint32_t)(warp % words);
+    const int64_t y = grow0 + b;
+    if (y <= 0 || y >= (int64_t)m0 - 1) {
+        return;   // warp-uniform: rows outside the grid or on its border are never edited
+    }
+    const uint32_t x = w * 32u + lane;
+    const bool interior = x > 0u && x < m1 - 1u;
+    uint32_t *word = mask + (uint64_t)b * mask_wpr + w;
+    const uint32_t old = *word;
+    bool is_free = (old >> lane) & 1u;
+    if (interior) {
+        float *cell = u + (uint64_t)b * pitch + x;
+        if (mode == 1) {
+            if (is_free) {
+                *cell = -1e6f;
+            }
+        } else {
+            const int o = occ[(uint64_t)(y - occ_row0) * m1 + x];
+            const bool goal = !is_free && *cell == 0.0f;
+            if (o != no_change && !goal) {
+                *cell = -1e6f;
+                is_free = o < threshold;
+            }
+        }
+    }
+    const uint32_t bits = __ballot_sync(0xffffffffu, is_free);
+    if (mode == 0 && lane == 0 && bits != old) {
+        *word = bits;
+    }
+}
+
 // The termination rule of harmonic_execute_gpu, evaluated right after a check sweep.
 // `it_after` = currentIteration after that sweep; `buffer` = ping-pong index that now holds the field.
 __global__ void decide_kernel(Ctrl *ctrl, float epsilon, uint32_t it_after, uint32_t m_max, uint32_t buffer)

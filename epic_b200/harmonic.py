@@ -126,6 +126,16 @@ class Harmonic(le.EpicHarmonic):
             return self._call("harmonic_utilities_set_cells_2d_gpu", int(numThreads), len(types), pv, pt)
         return self._call("harmonic_utilities_set_cells_2d_cpu", len(types), pv, pt)
 
+    def set_occupancy_grid(self, data, process='gpu', obstacleThreshold=50, noChangeValue=-2):
+        """Dense map ingest (extension): `data` is a nav_msgs/OccupancyGrid-style int8 array of the grid's shape."""
+        data = np.ascontiguousarray(data, dtype=np.int8)
+        assert data.shape == self.field.shape
+        return self._call("harmonic_utilities_set_occupancy_grid_2d_" + process, data.ctypes.data_as(ct.POINTER(ct.c_byte)),
+                          int(obstacleThreshold), int(noChangeValue))
+
+    def reset_free_cells(self, process='gpu'):
+        return self._call("harmonic_utilities_reset_free_cells_2d_" + process)
+
     # -- streamlines ---------------------------------------------------------------------------------
     def compute_potential(self, x, y, process='cpu'):
         out = ct.c_float(0.0)

@@ -148,6 +148,20 @@ EPIC_API int harmonic_compute_paths_2d_gpu(Harmonic *harmonic, unsigned int numP
                                            float stepSize, float cdPrecision, unsigned int maxLength, int *results,
                                            unsigned int *k, float **paths);
 
+
+/* ---- Extensions: dense map ingest.  The reference's node turns every /map message into a set_cells call
+ * over EVERY interior cell and implements "reset free cells" the same way (k = N scatter lists, 12 bytes per
+ * cell; src/epic_navigation_node_harmonic.cpp:383-426, :582-611).  These take the occupancy grid itself (one
+ * signed byte per cell, row-major like nav_msgs/OccupancyGrid.data) and classify it in place: value ==
+ * noChangeValue or a goal cell -> untouched; value >= obstacleThreshold -> obstacle; else free.  As with
+ * set_cells, a caller that mirrors the field on the host calls the _cpu twin too. ---- */
+EPIC_API int harmonic_utilities_set_occupancy_grid_2d_cpu(Harmonic *harmonic, const signed char *data,
+                                                          int obstacleThreshold, int noChangeValue);
+EPIC_API int harmonic_utilities_set_occupancy_grid_2d_gpu(Harmonic *harmonic, const signed char *data,
+                                                          int obstacleThreshold, int noChangeValue);
+EPIC_API int harmonic_utilities_reset_free_cells_2d_cpu(Harmonic *harmonic);
+EPIC_API int harmonic_utilities_reset_free_cells_2d_gpu(Harmonic *harmonic);
+
 #ifdef __cplusplus
 }  /* namespace epic */
 #endif
