@@ -45,15 +45,53 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks and throttle reasons sampled while the timed region runs."""
+    """SM clock and throttle reasons sampled while the timed region runs: NVML polled every few milliseconds
+    from a thread (the timed region of a multi-GPU run is only tens of milliseconds long), nvidia-smi as the
+    fallback when the NVML binding is missing."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.sm, self.max_sm, self.reasons = [], None, set()
+        self.nvml, self.handle, self.stop_flag, self.thread = None, None, False, None
+
+    def _poll(self):
+        n = self.nvml
+        names = (("hw_slowdown", getattr(n, "nvmlClocksEventReasonHwSlowdown", 0x8)),
+                 ("hw_thermal_slowdown", getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", 0x40)),
+                 ("sw_thermal_slowdown", getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", 0x20)),
+                 ("sw_power_cap", getattr(n, "nvmlClocksEventReasonSwPowerCap", 0x4)))
+        get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                mask = int(get_reasons(self.handle))
+                for name, bit in names:
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.004)
 
     def __enter__(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            idx = self.index
+            if vis and all(v.strip().isdigit() for v in vis.split(",")):
+                idx = int(vis.split(",")[self.index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return self
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -64,16 +102,25 @@ class ClockSampler:
             self.proc = None
         return self
 
+    def mark(self):
+        """Forget what was sampled so far (called right before the timed region starts)."""
+        self.sm, self.rows, self.reasons = [], [], set()
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def __exit__(self, *exc):
+        self.stop_flag = True
         if self.proc is not None:
             self.proc.terminate()
+        if self.thread is not None:
             self.thread.join(timeout=2)
 
     def summary(self):
+        if self.nvml is not None:
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_sm,
+                    "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml, 4 ms poll"}
         sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
         reasons = set()
@@ -83,7 +130,7 @@ class ClockSampler:
                     if v.lower().startswith("active"):
                         reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 def workload(args):
@@ -212,11 +259,13 @@ def run_native(args):
             launches0 = slab.launches()
             start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             barrier()
+            clocks.mark()
             start.record()
             for _ in range(args.steps):
                 solver.run(SWEEPS_PER_STEP, True)
             stop.record()
             barrier()
+            clocks.stop_flag = True
         ms = max_over_ranks(start.elapsed_time(stop))
         launches = slab.launches() - launches0
         value = updates_per_step * args.steps / (ms * 1e-3) / 1e9
