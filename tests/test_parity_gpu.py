@@ -304,3 +304,57 @@ def test_round_trip_and_idempotence_at_full_size(libepic_built):
     o.run_iterations(13)
     assert np.array_equal(b[:48], o.u[:48])
     f.close()
+
+
+def _random_state_band(shape, lo, hi, seed):
+    """Rows / layers [lo, hi) of a grid whose free cells hold arbitrary relaxed-looking values, so that every
+    cell moves from the first sweep on (a field of -1e6 with a few goals would leave most of a band untouched)."""
+    u, locked = grids.random_obstacles(shape, 0.2, 0, seed=seed, row0=lo, rows=hi - lo)
+    rng = np.random.RandomState([seed, lo])
+    vals = -40.0 * rng.random_sample(u.shape).astype(np.float32)
+    u = np.where(locked == 0, vals, u).astype(np.float32)
+    goals = (rng.random_sample(u.shape) < 1e-4) & (locked == 0)
+    inner = np.zeros(u.shape, bool)
+    inner[(slice(1, -1),) * u.ndim] = True
+    goals &= inner
+    u[goals] = 0.0
+    locked[goals] = 1
+    return u, locked
+
+
+def _check_bands(shape, bands, sweeps, seed):
+    f = Field(shape)
+    held = {}
+    for lo, hi in bands:
+        held[lo] = _random_state_band(shape, lo, hi, seed)
+        f.upload(*held[lo], first=lo, layers=hi - lo)
+    f.run(0, sweeps, check_last=False)
+    for lo, hi in bands:
+        u, locked = held[lo]
+        got = f.download_u(first=lo, layers=hi - lo)
+        # the oracle sees the band as a grid of its own: its first / last layers are never updated there,
+        # while on the device they are interior cells fed by the (empty) rest of the field -- compare the
+        # layers that `sweeps` sweeps cannot reach from such a cut; a cut on the global border is exact
+        o = orc.Oracle(u.copy(), locked.copy(), 1e-3, 1000, threads=8)
+        assert lo % 2 == 0, "the colour phase follows the global layer index"
+        o.run_iterations(sweeps)
+        a = 0 if lo == 0 else sweeps
+        b = (hi - lo) if hi == shape[0] else (hi - lo) - sweeps
+        assert np.array_equal(got[a:b], o.u[a:b]), "band %d..%d of %s differs from the oracle" % (lo, hi, shape)
+        assert not np.array_equal(got[a:b], u[a:b])
+    f.close()
+
+
+def test_maximum_size_2d_sampled_bands_against_oracle(libepic_built):
+    """65536 x 65536 (BASELINE.json config 4's size): N = 2^32 cells, one more than the reference's unsigned
+    int can count, 33 GiB resident.  Three row bands (top border, middle, bottom border) hold a
+    seeded state, the rest of the field stays empty; 12 half-sweeps (three passes) on the device must equal the
+    64-bit oracle on each band -- 64-bit addressing, tile indexing over 197 000 CTAs, border handling at row
+    65535."""
+    size = 65536
+    _check_bands((size, size), [(0, 192), (size // 2 - 96, size // 2 + 96), (size - 192, size)], 12, seed=77)
+
+
+def test_maximum_size_3d_sampled_slabs_against_oracle(libepic_built):
+    """1024^3 (BASELINE.json config 5): x0-slabs at the top border, in the middle and at the bottom border."""
+    _check_bands((1024, 1024, 1024), [(0, 20), (510, 530), (1004, 1024)], 6, seed=78)
