@@ -86,6 +86,7 @@ int epic_b200_field_info(epic_b200_field *f, epic_b200_info *info)
     info->tile_rows = (uint32_t)f->impl->tile_rows();
     info->math = (uint32_t)f->impl->math();
     info->device = f->impl->device();
+    info->skipped_tiles = f->impl->skipped_tiles();
     return 0;
 }
 

@@ -214,7 +214,11 @@ int Field::create(Field **out, unsigned n, const uint64_t *gm, uint64_t row0, ui
         if (!allow_smem(sweep2d_kernel<StrictMath, 256>, 227 * 1024) ||
             !allow_smem(sweep2d_kernel<FastMath, 256>, 227 * 1024) ||
             !allow_smem(sweep2d_kernel<StrictMath, 512>, 227 * 1024) ||
-            !allow_smem(sweep2d_kernel<FastMath, 512>, 227 * 1024)) {
+            !allow_smem(sweep2d_kernel<FastMath, 512>, 227 * 1024) ||
+            !allow_smem(sweep2d_kernel<StrictMath, 256, true>, 227 * 1024) ||
+            !allow_smem(sweep2d_kernel<FastMath, 256, true>, 227 * 1024) ||
+            !allow_smem(sweep2d_kernel<StrictMath, 512, true>, 227 * 1024) ||
+            !allow_smem(sweep2d_kernel<FastMath, 512, true>, 227 * 1024)) {
             cudaGetLastError();
             delete f;
             return kInvalidCudaParam;
@@ -282,6 +286,18 @@ int Field::create(Field **out, unsigned n, const uint64_t *gm, uint64_t row0, ui
     ok = ok && cudaMalloc(&f->freemask_, mbytes) == cudaSuccess && cudaMemset(f->freemask_, 0, mbytes) == cudaSuccess;
     ok = ok && cudaMalloc(&f->ctrl_, sizeof(Ctrl)) == cudaSuccess && cudaMemset(f->ctrl_, 0, sizeof(Ctrl)) == cudaSuccess;
     ok = ok && cudaMalloc(&f->flags_, 256) == cudaSuccess && cudaMemset(f->flags_, 0, 256) == cudaSuccess;
+    if (n == 2) {
+        const int HC = 4 * ((f->T_ + 3) / 4);
+        const uint64_t ntx = (gm[1] + (kTileW - 2 * HC) - 1) / (kTileW - 2 * HC);
+        const uint64_t nty = (rows + (f->TH_ - 2 * f->T_) - 1) / (f->TH_ - 2 * f->T_);
+        f->chg_bytes_ = (size_t)round_up(ntx * nty, 256);
+        for (int i = 0; i < 2 && ok; ++i) {
+            ok = cudaMalloc(&f->chg_[i], f->chg_bytes_) == cudaSuccess && cudaMemset(f->chg_[i], 1, f->chg_bytes_) == cudaSuccess;
+        }
+        if (const char *e = getenv("EPIC_SKIP_STATIC")) {
+            f->skip_static_ = atoi(e) != 0;
+        }
+    }
     ok = ok && cudaMallocHost(&f->ctrl_host_, sizeof(Ctrl) * kSlots) == cudaSuccess;
     if (ok) {
         memset(f->ctrl_host_, 0, sizeof(Ctrl) * kSlots);
@@ -332,6 +348,9 @@ Field::~Field()
             if (g.exec) cudaGraphExecDestroy(g.exec);
         }
         if (freemask_) cudaFree(freemask_);
+        for (int i = 0; i < 2; ++i) {
+            if (chg_[i]) cudaFree(chg_[i]);
+        }
         if (flags_) cudaFree(flags_);
         if (ctrl_) cudaFree(ctrl_);
         if (ctrl_host_) cudaFreeHost(ctrl_host_);
@@ -382,6 +401,7 @@ int Field::upload_u(const float *host, uint64_t first, uint64_t layers)
     if (host == nullptr || !range_ok(grow0_, buf_layers_, first, layers)) {
         return kInvalidData;
     }
+    chg_stale_ = true;
     DeviceGuard guard(cfg_.device);
     if (wait_peers() != kSuccess) {   // neighbours may still be storing into the ghost layers
         return kDeviceSynchronize;
@@ -439,6 +459,7 @@ int Field::upload_locked(const uint32_t *host, uint64_t first, uint64_t layers)
     if (host == nullptr || !range_ok(grow0_, buf_layers_, first, layers)) {
         return kInvalidData;
     }
+    chg_stale_ = true;
     DeviceGuard guard(cfg_.device);
     const uint64_t inner = gm_[n_ - 1];
     const uint64_t rows_per_layer = (n_ == 2) ? 1 : gm_[1];
@@ -690,6 +711,7 @@ int Field::launch_pass_2d(uint32_t it0, uint32_t count, bool check_last)
     p.out_w = kTileW - 2u * p.HC;
     p.ntx = (uint32_t)((gm_[1] + p.out_w - 1) / p.out_w);
     const uint32_t nty = (uint32_t)((rows_ + p.out_h - 1) / p.out_h);
+    p.nty = nty;
     p.count = count;
     p.parity0 = (uint32_t)(((int64_t)it0 + grow0_) & 1);
     p.check = check_last ? 1u : 0u;
@@ -712,27 +734,61 @@ int Field::launch_pass_2d(uint32_t it0, uint32_t count, bool check_last)
         if (!allow_smem(sweep2d_kernel<StrictMath, 256>, 227 * 1024) ||
             !allow_smem(sweep2d_kernel<FastMath, 256>, 227 * 1024) ||
             !allow_smem(sweep2d_kernel<StrictMath, 512>, 227 * 1024) ||
-            !allow_smem(sweep2d_kernel<FastMath, 512>, 227 * 1024)) {
+            !allow_smem(sweep2d_kernel<FastMath, 512>, 227 * 1024) ||
+            !allow_smem(sweep2d_kernel<StrictMath, 256, true>, 227 * 1024) ||
+            !allow_smem(sweep2d_kernel<FastMath, 256, true>, 227 * 1024) ||
+            !allow_smem(sweep2d_kernel<StrictMath, 512, true>, 227 * 1024) ||
+            !allow_smem(sweep2d_kernel<FastMath, 512, true>, 227 * 1024)) {
             cudaGetLastError();
             return kInvalidCudaParam;
         }
         attr_done_ = true;
     }
+    // Static-tile skipping: only inside solve() on a whole grid (no ghost layers, no peers).
+    const bool track = tracking_ && skip_static_ && ghost_ == 0 && !has_peers() && chg_[0] != nullptr &&
+                       (size_t)p.ntx * nty <= chg_bytes_;
+    if (track) {
+        if (chg_stale_) {
+            if (cudaMemsetAsync(chg_[0], 1, chg_bytes_, stream_) != cudaSuccess ||
+                cudaMemsetAsync(chg_[1], 1, chg_bytes_, stream_) != cudaSuccess) {
+                cudaGetLastError();
+                return kKernelExecution;
+            }
+            chg_stale_ = false;
+        }
+        p.chg_prev = chg_[cur_];
+        p.chg_out = chg_[cur_ ^ 1];
+        p.skipped = &ctrl_->skipped;
+    } else {
+        chg_stale_ = true;
+    }
     if (cfg_.math == MATH_STRICT) {
         StrictMath m;
         m.init(kLog4);
         if (NT_ == 512) {
-            sweep2d_kernel<StrictMath, 512><<<grid, 512, smem, stream_>>>(tmap_[cur_], p, m);
+            if (track) sweep2d_kernel<StrictMath, 512, true><<<grid, 512, smem, stream_>>>(tmap_[cur_], p, m);
+            else sweep2d_kernel<StrictMath, 512><<<grid, 512, smem, stream_>>>(tmap_[cur_], p, m);
         } else {
-            sweep2d_kernel<StrictMath, 256><<<grid, 256, smem, stream_>>>(tmap_[cur_], p, m);
+            if (track) sweep2d_kernel<StrictMath, 256, true><<<grid, 256, smem, stream_>>>(tmap_[cur_], p, m);
+            else sweep2d_kernel<StrictMath, 256><<<grid, 256, smem, stream_>>>(tmap_[cur_], p, m);
         }
     } else {
         FastMath m;
         m.ln2n = 1.3862943611198906f;
         if (NT_ == 512) {
-            sweep2d_kernel<FastMath, 512><<<grid, 512, smem, stream_>>>(tmap_[cur_], p, m);
+            if (track) sweep2d_kernel<FastMath, 512, true><<<grid, 512, smem, stream_>>>(tmap_[cur_], p, m);
+            else sweep2d_kernel<FastMath, 512><<<grid, 512, smem, stream_>>>(tmap_[cur_], p, m);
         } else {
-            sweep2d_kernel<FastMath, 256><<<grid, 256, smem, stream_>>>(tmap_[cur_], p, m);
+            if (track) sweep2d_kernel<FastMath, 256, true><<<grid, 256, smem, stream_>>>(tmap_[cur_], p, m);
+            else sweep2d_kernel<FastMath, 256><<<grid, 256, smem, stream_>>>(tmap_[cur_], p, m);
+        }
+    }
+    if (track && count < 2) {
+        // a pass of one half-sweep has only exercised one colour: its "nothing changed" proves nothing
+        // about the other one, so the next pass must not skip on these flags
+        if (cudaMemsetAsync(chg_[cur_ ^ 1], 1, chg_bytes_, stream_) != cudaSuccess) {
+            cudaGetLastError();
+            return kKernelExecution;
         }
     }
     launches_++;
@@ -936,6 +992,11 @@ int Field::solve(float epsilon, uint32_t stagger, uint32_t m_max, uint32_t *iter
         return kInvalidData;
     }
     DeviceGuard guard(cfg_.device);
+    struct Tracking {   // static-tile skipping is on for the passes this function issues
+        bool &flag;
+        explicit Tracking(bool &f) : flag(f) { flag = true; }
+        ~Tracking() { flag = false; }
+    } tracking(tracking_);
     if (cudaMemsetAsync(ctrl_, 0, sizeof(Ctrl), stream_) != cudaSuccess) {
         cudaGetLastError();
         return kMemcpyToDevice;
@@ -990,6 +1051,7 @@ int Field::solve(float epsilon, uint32_t stagger, uint32_t m_max, uint32_t *iter
         return kDeviceSynchronize;
     }
     cur_ = (int)fin->final_buffer;
+    skipped_tiles_ += fin->skipped;
     *iteration = fin->final_iteration;
     *delta = fin->last_delta;
     // leave the flag clear so that later update / update_and_check calls sweep again
@@ -1008,6 +1070,7 @@ int Field::set_cells_2d(uint32_t k, const uint32_t *v, const uint32_t *types)
     if (n_ != 2 || k == 0 || v == nullptr || types == nullptr) {
         return kInvalidData;
     }
+    chg_stale_ = true;
     DeviceGuard guard(cfg_.device);
     // The reference's CPU twin applies the edits in order; when a cell appears more than once the
     // last edit wins.  last[i] = index of the last *valid* edit of the cell edit i targets.
@@ -1060,6 +1123,7 @@ int Field::ingest_occupancy_2d(const signed char *host, uint64_t first, uint64_t
     if (n_ != 2 || host == nullptr || !range_ok(grow0_, buf_layers_, first, layers)) {
         return kInvalidData;
     }
+    chg_stale_ = true;
     DeviceGuard guard(cfg_.device);
     if (wait_peers() != kSuccess) {
         return kDeviceSynchronize;
@@ -1100,6 +1164,7 @@ int Field::reset_free_cells_2d()
     if (n_ != 2) {
         return kInvalidData;
     }
+    chg_stale_ = true;
     DeviceGuard guard(cfg_.device);
     if (wait_peers() != kSuccess) {
         return kDeviceSynchronize;

@@ -122,6 +122,7 @@ public:
     uint64_t launches() const { return launches_; }
     int tile_rows() const { return TH_; }
     size_t device_bytes() const { return device_bytes_; }
+    uint64_t skipped_tiles() const { return skipped_tiles_; }   // by static-tile skipping, over all solves
 
 private:
     Field() {}
@@ -151,6 +152,15 @@ private:
     };
     PeriodGraph graphs_[4];
     bool graphs_off_ = false;
+    // Static-tile skipping (2-D whole-grid solves, see Sweep2DParams::chg_prev): two flag arrays that swap
+    // with the ping-pong buffers.  `tracking_` is on inside solve(); any other writer of the field (plain
+    // run(), uploads, edits) leaves the flags stale, and the next tracked pass resets them to "changed".
+    uint8_t *chg_[2] = {nullptr, nullptr};
+    size_t chg_bytes_ = 0;
+    bool tracking_ = false;
+    bool chg_stale_ = true;
+    bool skip_static_ = true;    // EPIC_SKIP_STATIC=0 turns the feature off
+    uint64_t skipped_tiles_ = 0;
 
     FieldConfig cfg_;
     unsigned n_ = 0;

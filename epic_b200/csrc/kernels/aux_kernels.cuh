@@ -29,7 +29,8 @@ struct Ctrl {                      // device-resident control block
     uint32_t iteration;            // currentIteration as the device sees it (replayed solver periods advance it)
     float epsilon;                 // termination rule of the solve in progress: delta < epsilon ...
     uint32_t m_max;                // ... and currentIteration >= m_max
-    uint32_t pad[2];
+    uint32_t skipped;              // tiles that returned early as static during the solve in progress
+    uint32_t pad;
 };
 
 // One warp packs 32 consecutive cells of one row into one mask word (ballot), coalesced reads.

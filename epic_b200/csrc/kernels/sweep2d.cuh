@@ -54,6 +54,15 @@ struct Sweep2DParams {
     float *peer_up;            // row 0 of the upper neighbour's ghost-below region in ITS destination buffer
     float *peer_down;          // row 0 of the lower neighbour's ghost-above region
     uint32_t halo_rows;
+    // Static-tile skipping (TRACK kernels, single-slab solves): one byte per tile, "some update of the
+    // previous pass changed a value in this tile".  A tile whose 3 x 3 neighbourhood is all-zero replays a
+    // computation that changed nothing, on the same input, into a buffer that already holds that data: it
+    // returns at once.  Bit-identical by construction; the delta of a skipped tile is 0 because no sweep of
+    // the previous pass moved any of its cells.
+    const uint8_t *chg_prev;   // flags written by the previous pass
+    uint8_t *chg_out;          // flags of this pass
+    uint32_t *skipped;         // statistics: tiles skipped (device counter)
+    uint32_t nty;              // rows of tiles
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
@@ -111,7 +120,7 @@ inline size_t sweep2d_smem_bytes(uint32_t TH, uint32_t NT)
 
 // One tile row for one lane: update the active colour of `cur` (in place) from the row above (`up`,
 // already holding this sweep's values of the other colour) and the row below (`dn`), store it.
-template <class Math>
+template <class Math, bool TRACK>
 struct RowCtx {
     const Math &math;
     float *tile;
@@ -120,6 +129,7 @@ struct RowCtx {
     bool checking;     // this sweep accumulates delta and this lane's columns are in the output region
     int T, TH, own_lo, own_hi;
     float dmax;
+    bool chg;          // TRACK: some update of this lane changed a value
 
     template <bool EVEN_COLS, bool CHECK>
     __device__ __forceinline__ void row(int r, const float4 &up, float4 &cur, const float4 &dn)
@@ -139,6 +149,10 @@ struct RowCtx {
             const float nz = math.update4(up.z, dn.z, cur.y, cur.w);
             if (active & 1u) nw.x = nx;
             if (active & 4u) nw.z = nz;
+            if (TRACK) {
+                chg = chg || (__float_as_uint(nw.x) != __float_as_uint(cur.x)) ||
+                      (__float_as_uint(nw.z) != __float_as_uint(cur.z));
+            }
         } else {
             float right = __shfl_down_sync(0xffffffffu, cur.x, 1);
             if (lane == 31 && col + 4 < kTileW) {
@@ -148,6 +162,10 @@ struct RowCtx {
             const float nq = math.update4(up.w, dn.w, cur.z, right);
             if (active & 2u) nw.y = ny;
             if (active & 8u) nw.w = nq;
+            if (TRACK) {
+                chg = chg || (__float_as_uint(nw.y) != __float_as_uint(cur.y)) ||
+                      (__float_as_uint(nw.w) != __float_as_uint(cur.w));
+            }
         }
         if (CHECK && checking) {
             const int b = by0 + r;
@@ -219,12 +237,34 @@ struct RowCtx {
     }
 };
 
-template <class Math, int NT>
+template <class Math, int NT, bool TRACK = false>
 __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1))
 sweep2d_kernel(const __grid_constant__ CUtensorMap src_map, const Sweep2DParams p, const Math math_in)
 {
     if (*p.ctrl_done) {
         return;  // a previous check sweep already met the termination rule
+    }
+    if (TRACK) {
+        // every thread reads the same nine bytes (broadcast, L2 hits): the decision is CTA-uniform
+        const int ttx = blockIdx.x % p.ntx, tty = blockIdx.x / p.ntx;
+        uint32_t any = 0;
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy) {
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int x = ttx + dx, y = tty + dy;
+                if (x >= 0 && x < (int)p.ntx && y >= 0 && y < (int)p.nty) {
+                    any |= p.chg_prev[y * (int)p.ntx + x];
+                }
+            }
+        }
+        if (any == 0) {
+            if (threadIdx.x == 0) {
+                p.chg_out[blockIdx.x] = 0;
+                atomicAdd(p.skipped, 1u);
+            }
+            return;
+        }
     }
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *tile = reinterpret_cast<float *>(smem_raw);
@@ -301,6 +341,7 @@ sweep2d_kernel(const __grid_constant__ CUtensorMap src_map, const Sweep2DParams 
     const int grp = panel * 32 + lane;
     const bool col_out = (col >= (int)p.HC) && (col < kTileW - (int)p.HC) && (gx0 + col < (int)p.m1);
     float dmax = 0.0f;
+    bool chg = false;
 
     for (uint32_t t = 0; t < p.count; ++t) {
         // rows that still matter for the output region after the remaining sweeps
@@ -313,16 +354,23 @@ sweep2d_kernel(const __grid_constant__ CUtensorMap src_map, const Sweep2DParams 
         const bool checking = p.check && (t + 1 == p.count);
 
         if (ra < rb) {
-            RowCtx<Math> cx{math, tile, lockt, col, grp, lane, by0, checking && col_out, (int)p.T, (int)p.TH,
-                            (int)p.own_lo, (int)p.own_hi, dmax};
+            RowCtx<Math, TRACK> cx{math, tile, lockt, col, grp, lane, by0, checking && col_out, (int)p.T, (int)p.TH,
+                                   (int)p.own_lo, (int)p.own_hi, dmax, chg};
             if (checking) {
                 cx.template band<true>(ra, rb, pb);
             } else {
                 cx.template band<false>(ra, rb, pb);
             }
             dmax = cx.dmax;
+            chg = cx.chg;
         }
         __syncthreads();
+    }
+    if (TRACK) {
+        const int any = __syncthreads_or(chg ? 1 : 0);
+        if (tid == 0) {
+            p.chg_out[blockIdx.x] = any ? 1 : 0;
+        }
     }
 
     // Write the output region (all of it, locked cells included: dst is a different buffer).

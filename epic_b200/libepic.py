@@ -47,7 +47,7 @@ class EpicHarmonic(ct.Structure):
 class FieldInfo(ct.Structure):
     _fields_ = [("pitch", ct.c_uint64), ("layer_floats", ct.c_uint64), ("launches", ct.c_uint64),
                 ("device_bytes", ct.c_uint64), ("sweeps_per_pass", ct.c_uint32), ("tile_rows", ct.c_uint32),
-                ("math", ct.c_uint32), ("device", ct.c_int32)]
+                ("math", ct.c_uint32), ("device", ct.c_int32), ("skipped_tiles", ct.c_uint64)]
 
 
 def build(force=False):

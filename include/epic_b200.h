@@ -35,6 +35,7 @@ typedef struct epic_b200_info {
     uint32_t tile_rows;      /* rows of the shared-memory tile (2-D) */
     uint32_t math;           /* EPIC_B200_MATH_* in effect */
     int32_t device;
+    uint64_t skipped_tiles;  /* tiles the solves so far skipped as static (bit-identical results either way) */
 } epic_b200_info;
 
 /* n = 2 or 3; m[n] = GLOBAL dimensions; the slab owns x0 in [row0, row0+rows) and keeps `ghost`

@@ -358,3 +358,26 @@ def test_maximum_size_2d_sampled_bands_against_oracle(libepic_built):
 def test_maximum_size_3d_sampled_slabs_against_oracle(libepic_built):
     """1024^3 (BASELINE.json config 5): x0-slabs at the top border, in the middle and at the bottom border."""
     _check_bands((1024, 1024, 1024), [(0, 20), (510, 530), (1004, 1024)], 6, seed=78)
+
+
+def test_static_tile_skipping_is_bit_identical_and_active(libepic_built, monkeypatch):
+    """Field::solve skips tiles whose 3x3 neighbourhood saw no update change a value in the previous pass
+    (the replayed computation is a no-op into a buffer that already holds the data).  Same iteration count,
+    delta and field with the feature off, and the feature must actually engage on a grid whose wave fronts
+    take a while to fill it."""
+    shape = (1536, 2048)
+    u, locked = grids.random_obstacles(shape, 0.2, 3, seed=9)
+    out = {}
+    for skip in ("0", "1"):
+        monkeypatch.setenv("EPIC_SKIP_STATIC", skip)
+        f = Field(shape)
+        f.upload(u, locked)
+        it, delta = f.solve(1e-3, 100)
+        out[skip] = (it, delta, common.sha1(f.download_u()), f.info()["skipped_tiles"])
+        # a second solve on the converged field: nearly everything is static from the second pass on
+        it2, delta2 = f.solve(1e-3, 100)
+        out[skip] += (it2, delta2, common.sha1(f.download_u()), f.info()["skipped_tiles"])
+        f.close()
+    assert out["0"][:3] == out["1"][:3] and out["0"][4:7] == out["1"][4:7]
+    assert out["0"][3] == 0 and out["0"][7] == 0
+    assert out["1"][3] > 0 and out["1"][7] > out["1"][3]
