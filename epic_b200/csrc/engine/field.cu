@@ -297,6 +297,9 @@ int Field::create(Field **out, unsigned n, const uint64_t *gm, uint64_t row0, ui
         if (const char *e = getenv("EPIC_SKIP_STATIC")) {
             f->skip_static_ = atoi(e) != 0;
         }
+        if (const char *e = getenv("EPIC_P2P_SYNC")) {
+            f->kernel_sync_ = strcmp(e, "stream") != 0;
+        }
     }
     ok = ok && cudaMallocHost(&f->ctrl_host_, sizeof(Ctrl) * kSlots) == cudaSuccess;
     if (ok) {
@@ -726,7 +729,25 @@ int Field::launch_pass_2d(uint32_t it0, uint32_t count, bool check_last)
     if (peer_[1].on) {
         p.peer_down = peer_[1].u[cur_ ^ 1] + (peer_[1].own_lo - p.halo_rows) * pitch_;
     }
-    if (wait_peers() != kSuccess) {
+    const bool kernel_sync = has_peers() && kernel_sync_;
+    if (kernel_sync) {
+        // passes are ordered between the GPUs inside the kernel (see Sweep2DParams::p2p_sync)
+        p.p2p_sync = 1;
+        p.pass_index = pass_count_ + 1;
+        p.wait_up = flags_ + 0;
+        p.wait_dn = flags_ + 1;
+        p.signal_up = peer_[0].on ? peer_[0].flags + 1 : nullptr;   // the upper neighbour's "from below" word
+        p.signal_dn = peer_[1].on ? peer_[1].flags + 0 : nullptr;
+        p.edge_count = flags_ + 2;
+        p.n_edge_up = p.ntx;
+        uint32_t rows_dn = 0;
+        for (uint32_t ty = 0; ty < nty; ++ty) {
+            if ((int64_t)own_lo_ + (int64_t)ty * p.out_h - p.T + p.TH > (int64_t)own_hi_) {
+                rows_dn++;
+            }
+        }
+        p.n_edge_dn = rows_dn * p.ntx;
+    } else if (wait_peers() != kSuccess) {
         return kKernelExecution;
     }
 
@@ -796,6 +817,10 @@ int Field::launch_pass_2d(uint32_t it0, uint32_t count, bool check_last)
         return kKernelExecution;
     }
     cur_ ^= 1;
+    if (kernel_sync) {
+        pass_count_++;      // the kernel's edge tiles publish it to the neighbours
+        return kSuccess;
+    }
     return signal_peers();
 }
 

@@ -203,6 +203,8 @@ private:
     Peer peer_[2];
     uint32_t *flags_ = nullptr;  // device: {from_up, from_down} = passes completed by the neighbours
     uint32_t pass_count_ = 0;    // passes issued by this slab
+    bool kernel_sync_ = true;    // 2-D: order passes between GPUs inside the sweep kernel (EPIC_P2P_SYNC=stream: by
+                                 // stream memory operations around it, as the 3-D path does)
     int wait_peers();            // enqueue: flags_[d] >= pass_count_ for every peer
     int signal_peers();          // enqueue: neighbour flags <- pass_count_
     void close_peers();

@@ -59,6 +59,20 @@ struct Sweep2DParams {
     // computation that changed nothing, on the same input, into a buffer that already holds that data: it
     // returns at once.  Bit-identical by construction; the delta of a skipped tile is 0 because no sweep of
     // the previous pass moved any of its cells.
+    // In-kernel ordering of passes between neighbouring GPUs (p2p_sync != 0).  The tile rows that touch a
+    // neighbour (they read its ghost rows and store into its ghost rows) run FIRST; each of them waits until
+    // that neighbour's flag word says its edge tiles finished the previous pass, and the last edge tile of a
+    // side to finish publishes this pass's index in the neighbour's flag word (system-scope release after
+    // every thread fenced its peer stores).  Interior tiles never wait, so the latency of the exchange hides
+    // behind them, and in the steady state the edge tiles find their flag already set.
+    uint32_t p2p_sync;
+    uint32_t pass_index;             // 1-based index of this pass on this slab
+    const uint32_t *wait_up;         // this slab's flag words: written by the upper / lower neighbour
+    const uint32_t *wait_dn;
+    uint32_t *signal_up;             // the neighbours' flag words for this slab
+    uint32_t *signal_dn;
+    uint32_t *edge_count;            // two local counters: edge tiles of this pass finished, per side
+    uint32_t n_edge_up, n_edge_dn;   // edge tiles per side
     const uint8_t *chg_prev;   // flags written by the previous pass
     uint8_t *chg_out;          // flags of this pass
     uint32_t *skipped;         // statistics: tiles skipped (device counter)
@@ -116,6 +130,27 @@ __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap *map, int x, i
 inline size_t sweep2d_smem_bytes(uint32_t TH, uint32_t NT)
 {
     return (size_t)TH * kTileW * sizeof(float) + (size_t)TH * kGroups + sizeof(MathTables) + 8 + (NT / 32) * sizeof(float);
+}
+
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Tile row of launch-order row r: with p2p_sync the first and the last two tile rows come first.
+__device__ __forceinline__ int tile_row_of(int r, int nty, bool edge_first)
+{
+    if (!edge_first || nty <= 3) {
+        return r;
+    }
+    return r == 0 ? 0 : (r == 1 ? nty - 1 : (r == 2 ? nty - 2 : r - 2));
 }
 
 // One tile row for one lane: update the active colour of `cur` (in place) from the row above (`up`,
@@ -278,22 +313,43 @@ sweep2d_kernel(const __grid_constant__ CUtensorMap src_map, const Sweep2DParams 
     // trip counts then live in uniform registers and the warp-synchronous operations in the row loop need
     // no convergence checks
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-    const int tx = blockIdx.x % p.ntx, ty = blockIdx.x / p.ntx;
+    const bool p2p = p.p2p_sync != 0;
+    const int tx = blockIdx.x % p.ntx, ty = tile_row_of(blockIdx.x / p.ntx, (int)p.nty, p2p);
     const int gx0 = tx * (int)p.out_w - (int)p.HC;                 // grid column of tile column 0
     const int by0 = (int)p.own_lo + ty * (int)p.out_h - (int)p.T;  // buffer row of tile row 0
+    // does this tile read the ghost rows of / store into a neighbour?
+    const bool edge_up = p2p && p.signal_up != nullptr && by0 < (int)p.own_lo;
+    const bool edge_dn = p2p && p.signal_dn != nullptr && by0 + (int)p.TH > (int)p.own_hi;
 
     if (tid == 0) {
         mbar_init(bar, 1);
+        if (edge_up) {
+            while (ld_acquire_sys(p.wait_up) + 1u < p.pass_index) {
+                __nanosleep(64);
+            }
+        }
+        if (edge_dn) {
+            while (ld_acquire_sys(p.wait_dn) + 1u < p.pass_index) {
+                __nanosleep(64);
+            }
+        }
+        if (edge_up || edge_dn) {
+            // the ghost rows were written by another GPU's generic-proxy stores; the tile load below reads
+            // them through the async proxy
+            asm volatile("fence.proxy.async;" ::: "memory");
+        }
     }
     __syncthreads();
     if (tid == 0) {
         mbar_expect_tx(bar, p.TH * kTileW * (uint32_t)sizeof(float));
         tma_load_2d(tile, &src_map, gx0, by0, bar);
-        // Warm L2 with the tile the CTA that follows this one on the SM will ask for.
+        // Warm L2 with the tile the CTA that follows this one on the SM will ask for (never a tile that is
+        // still waiting for a neighbour: edge tiles are at the front of the launch order).
         const uint32_t nb = blockIdx.x + p.prefetch_stride;
         if (nb < gridDim.x) {
+            const int nty_row = tile_row_of((int)(nb / p.ntx), (int)p.nty, p2p);
             tma_prefetch_2d(&src_map, (int)(nb % p.ntx) * (int)p.out_w - (int)p.HC,
-                            (int)p.own_lo + (int)(nb / p.ntx) * (int)p.out_h - (int)p.T);
+                            (int)p.own_lo + nty_row * (int)p.out_h - (int)p.T);
         }
     }
 
@@ -402,6 +458,23 @@ sweep2d_kernel(const __grid_constant__ CUtensorMap src_map, const Sweep2DParams 
                         *reinterpret_cast<float4 *>(lrow + c) = v;
                     }
                 }
+            }
+        }
+    }
+
+    if (edge_up || edge_dn) {
+        __threadfence_system();     // this thread's stores into the neighbour are visible system-wide ...
+        __syncthreads();            // ... for every thread of the CTA before thread 0 counts the tile as done
+        if (tid == 0) {
+            if (edge_up && atomicAdd(p.edge_count + 0, 1u) + 1u == p.n_edge_up) {
+                p.edge_count[0] = 0u;   // the next pass starts after this kernel has ended
+                __threadfence_system();
+                st_release_sys(p.signal_up, p.pass_index);
+            }
+            if (edge_dn && atomicAdd(p.edge_count + 1, 1u) + 1u == p.n_edge_dn) {
+                p.edge_count[1] = 0u;
+                __threadfence_system();
+                st_release_sys(p.signal_dn, p.pass_index);
             }
         }
     }

@@ -7,9 +7,9 @@ nvidia-smi -L | wc -l
 timeout 600 python -m pytest tests/test_sharded_gpu.py -m gpu -q -x --timeout 500 -k nccl 2>&1 | tail -3
 for N in $NS; do
   if [ "$N" = "1" ]; then
-    timeout 900 python bench.py --gpus 1 --steps $STEPS --warmup 3 --no-cpu $EXTRA > gpurun_out/scale_n$N.json 2> gpurun_out/scale_n$N.err
+    timeout 400 python bench.py --gpus 1 --steps $STEPS --warmup 3 --no-cpu $EXTRA > gpurun_out/scale_n$N.json 2> gpurun_out/scale_n$N.err
   else
-    timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2961$N \
+    timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2961$N \
       bench.py --gpus $N --steps $STEPS --warmup 3 --no-cpu $EXTRA > gpurun_out/scale_n$N.json 2> gpurun_out/scale_n$N.err
   fi
   python - <<PY
