@@ -7,9 +7,11 @@
  * layers.  This header exposes the slab object that libepic's entry points are themselves built on
  * (the reference functions it generalises: libepic/src/harmonic/harmonic_model_gpu.cu:34-204 for
  * residency, harmonic_gpu.cu:327-434 for update / update_and_check / get_potential_values,
- * harmonic_utilities_gpu.cu:66-138 for set_cells).  Halo exchange and the max-reduction of delta are
- * the caller's (epic_b200/sharded.py does them with torch.distributed over NCCL); nothing in here
- * talks to another device.
+ * harmonic_utilities_gpu.cu:66-138 for set_cells).  The max-reduction of delta over the ranks is the
+ * caller's (epic_b200/sharded.py: one all-reduce per check sweep); ghost layers are refreshed either by the
+ * caller (NCCL send/recv on the pointers epic_b200_field_layer_ptr returns) or by the library itself once the
+ * neighbouring slabs have been introduced with the peer calls below (NVLink peer stores from inside the sweep
+ * kernel).
  *
  * Plain C: pointers and sizes only.  Return values are libepic's error codes (0 = success).
  */
@@ -63,7 +65,7 @@ int epic_b200_field_solve(epic_b200_field *f, float epsilon, uint32_t stagger, u
 int epic_b200_field_sync(epic_b200_field *f);
 
 /* Device address of global layer `layer` in the buffer that currently holds the field (it changes
- * with every pass in 2-D: query after each run).  Null when the layer is not held by this slab. */
+ * with every pass: query after each run).  Null when the layer is not held by this slab. */
 void *epic_b200_field_layer_ptr(epic_b200_field *f, int64_t layer);
 
 /* Peer-to-peer halos over NVLink (one process per GPU on one node).  peer_export fills an opaque blob
