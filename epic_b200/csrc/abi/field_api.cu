@@ -90,6 +90,15 @@ int epic_b200_field_info(epic_b200_field *f, epic_b200_info *info)
     return 0;
 }
 
+int epic_b200_field_set_tracking(epic_b200_field *f, int on)
+{
+    if (f == nullptr) {
+        return 2;
+    }
+    f->impl->set_tracking(on != 0);
+    return 0;
+}
+
 int epic_b200_field_upload_u(epic_b200_field *f, const float *host, uint64_t first, uint64_t layers)
 {
     return f ? f->impl->upload_u(host, first, layers) : 2;

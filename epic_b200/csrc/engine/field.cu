@@ -765,9 +765,9 @@ int Field::launch_pass_2d(uint32_t it0, uint32_t count, bool check_last)
         }
         attr_done_ = true;
     }
-    // Static-tile skipping: only inside solve() on a whole grid (no ghost layers, no peers).
-    const bool track = tracking_ && skip_static_ && ghost_ == 0 && !has_peers() && chg_[0] != nullptr &&
-                       (size_t)p.ntx * nty <= chg_bytes_;
+    // Static-tile skipping: inside solve(), or when the driver of a sharded solve has switched it on
+    // (set_tracking); tiles that read ghost layers always run, see the kernel.
+    const bool track = tracking_ && skip_static_ && chg_[0] != nullptr && (size_t)p.ntx * nty <= chg_bytes_;
     if (track) {
         if (chg_stale_) {
             if (cudaMemsetAsync(chg_[0], 1, chg_bytes_, stream_) != cudaSuccess ||
@@ -1008,6 +1008,7 @@ int Field::read_delta(float *delta)
         return kDeviceSynchronize;
     }
     *delta = ctrl_host_[0].last_delta;
+    skipped_tiles_ += ctrl_host_[0].taken_skipped;
     return kSuccess;
 }
 

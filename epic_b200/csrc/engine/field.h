@@ -107,6 +107,12 @@ public:
     int set_peer_local(int dir, Field *other);            // neighbour lives in this process
     bool has_peers() const { return peer_[0].on || peer_[1].on; }
 
+    // Static-tile skipping for the passes run() issues from now on (solve() switches it on by itself).  The
+    // caller promises that nothing but these passes and the neighbours' halo stores touches the field in
+    // between; uploads and edits reset the bookkeeping on their own.  Meant for sharded solves to epsilon;
+    // throughput measurements leave it off so that every tile is swept.
+    void set_tracking(bool on) { tracking_ = on; }
+
     int sync();
     cudaStream_t stream() const { return stream_; }
     int sweeps_per_pass() const { return T_; }

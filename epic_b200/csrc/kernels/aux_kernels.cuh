@@ -29,8 +29,8 @@ struct Ctrl {                      // device-resident control block
     uint32_t iteration;            // currentIteration as the device sees it (replayed solver periods advance it)
     float epsilon;                 // termination rule of the solve in progress: delta < epsilon ...
     uint32_t m_max;                // ... and currentIteration >= m_max
-    uint32_t skipped;              // tiles that returned early as static during the solve in progress
-    uint32_t pad;
+    uint32_t skipped;              // tiles that returned early as static since the counter was last taken
+    uint32_t taken_skipped;        // take_delta_kernel moves `skipped` here for the host to read
 };
 
 // One warp packs 32 consecutive cells of one row into one mask word (ballot), coalesced reads.
@@ -210,6 +210,8 @@ __global__ void take_delta_kernel(Ctrl *ctrl, uint32_t it_after)
     ctrl->last_delta = __uint_as_float(ctrl->delta_bits);
     ctrl->delta_bits = 0u;
     ctrl->last_check_iteration = it_after;
+    ctrl->taken_skipped = ctrl->skipped;
+    ctrl->skipped = 0u;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -279,15 +279,20 @@ sweep2d_kernel(const __grid_constant__ CUtensorMap src_map, const Sweep2DParams 
     if (*p.ctrl_done) {
         return;  // a previous check sweep already met the termination rule
     }
+    const bool p2p = p.p2p_sync != 0;
+    const int tx = blockIdx.x % p.ntx, ty = tile_row_of(blockIdx.x / p.ntx, (int)p.nty, p2p);
+    const int by0 = (int)p.own_lo + ty * (int)p.out_h - (int)p.T;  // buffer row of tile row 0
     if (TRACK) {
-        // every thread reads the same nine bytes (broadcast, L2 hits): the decision is CTA-uniform
-        const int ttx = blockIdx.x % p.ntx, tty = blockIdx.x / p.ntx;
-        uint32_t any = 0;
+        // Tiles that read ghost rows (their input is also written by a neighbouring slab) always run.  For the
+        // others every thread reads the same nine bytes (broadcast, L2 hits): the decision is CTA-uniform.
+        const bool reads_ghost = (by0 < (int)p.own_lo && p.grow0 + (int)p.own_lo > 0) ||
+                                 (by0 + (int)p.TH > (int)p.own_hi && p.grow0 + (int)p.own_hi < (int)p.m0);
+        uint32_t any = reads_ghost ? 1u : 0u;
 #pragma unroll
         for (int dy = -1; dy <= 1; ++dy) {
 #pragma unroll
             for (int dx = -1; dx <= 1; ++dx) {
-                const int x = ttx + dx, y = tty + dy;
+                const int x = tx + dx, y = ty + dy;
                 if (x >= 0 && x < (int)p.ntx && y >= 0 && y < (int)p.nty) {
                     any |= p.chg_prev[y * (int)p.ntx + x];
                 }
@@ -295,7 +300,7 @@ sweep2d_kernel(const __grid_constant__ CUtensorMap src_map, const Sweep2DParams 
         }
         if (any == 0) {
             if (threadIdx.x == 0) {
-                p.chg_out[blockIdx.x] = 0;
+                p.chg_out[ty * (int)p.ntx + tx] = 0;
                 atomicAdd(p.skipped, 1u);
             }
             return;
@@ -313,10 +318,7 @@ sweep2d_kernel(const __grid_constant__ CUtensorMap src_map, const Sweep2DParams 
     // trip counts then live in uniform registers and the warp-synchronous operations in the row loop need
     // no convergence checks
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-    const bool p2p = p.p2p_sync != 0;
-    const int tx = blockIdx.x % p.ntx, ty = tile_row_of(blockIdx.x / p.ntx, (int)p.nty, p2p);
     const int gx0 = tx * (int)p.out_w - (int)p.HC;                 // grid column of tile column 0
-    const int by0 = (int)p.own_lo + ty * (int)p.out_h - (int)p.T;  // buffer row of tile row 0
     // does this tile read the ghost rows of / store into a neighbour?
     const bool edge_up = p2p && p.signal_up != nullptr && by0 < (int)p.own_lo;
     const bool edge_dn = p2p && p.signal_dn != nullptr && by0 + (int)p.TH > (int)p.own_hi;
@@ -425,7 +427,7 @@ sweep2d_kernel(const __grid_constant__ CUtensorMap src_map, const Sweep2DParams 
     if (TRACK) {
         const int any = __syncthreads_or(chg ? 1 : 0);
         if (tid == 0) {
-            p.chg_out[blockIdx.x] = any ? 1 : 0;
+            p.chg_out[ty * (int)p.ntx + tx] = any ? 1 : 0;
         }
     }
 

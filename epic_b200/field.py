@@ -100,6 +100,10 @@ class Field:
                                                              ct.byref(d)))
         return it.value, d.value
 
+    def set_tracking(self, on):
+        """Static-tile skipping for the passes run() issues from now on (bit-identical; see epic_b200.h)."""
+        self._check("set_tracking", self._lib.epic_b200_field_set_tracking(self._h, 1 if on else 0))
+
     def sync(self):
         self._check("sync", self._lib.epic_b200_field_sync(self._h))
 

@@ -128,6 +128,7 @@ EXTENSION_EXPORTS = {
     "epic_b200_field_read_delta": (_F, _P(ct.c_float)),
     "epic_b200_field_solve": (_F, ct.c_float, ct.c_uint32, ct.c_uint32, _P(ct.c_uint32), _P(ct.c_float)),
     "epic_b200_field_sync": (_F,),
+    "epic_b200_field_set_tracking": (_F, ct.c_int),
     "epic_b200_field_set_cells_2d": (_F, ct.c_uint32, _P(ct.c_uint32), _P(ct.c_uint32)),
     "epic_b200_field_potential_2d": (_F, ct.c_float, ct.c_float, _P(ct.c_float)),
     "epic_b200_field_gradient_2d": (_F, ct.c_float, ct.c_float, ct.c_float, _P(ct.c_float), _P(ct.c_float)),

@@ -93,6 +93,10 @@ class GpuSlab:
     def run_pass(self, it0, count, check_last):
         self.field.run(it0, count, check_last)
 
+    def set_tracking(self, on):
+        """Static-tile skipping (bit-identical, see include/epic_b200.h) for the passes that follow."""
+        self.field.set_tracking(on)
+
     def read_delta(self):
         return self.field.read_delta()
 
@@ -199,11 +203,17 @@ class ShardedSolver:
             raise ValueError("epsilon must be positive and stagger non-zero")
         m_max = max(self.slab.shape) if m_max is None else m_max
         self.iteration = 0
-        while True:
-            to_check = (-self.iteration) % stagger
-            self.run(to_check + 1, True)
-            if self.delta < epsilon and self.iteration >= m_max:
-                return self.iteration, self.delta
+        if len(self.slab.shape) == 2 and hasattr(self.slab, "set_tracking"):
+            self.slab.set_tracking(True)     # tiles that stopped changing (and do not read ghost rows) are skipped
+        try:
+            while True:
+                to_check = (-self.iteration) % stagger
+                self.run(to_check + 1, True)
+                if self.delta < epsilon and self.iteration >= m_max:
+                    return self.iteration, self.delta
+        finally:
+            if len(self.slab.shape) == 2 and hasattr(self.slab, "set_tracking"):
+                self.slab.set_tracking(False)
 
 
 def gather_field(slab, group=None):

@@ -63,6 +63,11 @@ int epic_b200_field_read_delta(epic_b200_field *f, float *delta);
 int epic_b200_field_solve(epic_b200_field *f, float epsilon, uint32_t stagger, uint32_t m_max, uint32_t *iterations,
                           float *delta);
 int epic_b200_field_sync(epic_b200_field *f);
+/* Static-tile skipping for the passes epic_b200_field_run issues from now on (2-D; field_solve uses it on its
+ * own): a tile whose 3 x 3 neighbourhood saw no update change a value in the previous pass returns at once --
+ * bit-identical results, less work on fields that are unreached or converged in places.  Tiles that read ghost
+ * layers always run.  Leave it off for throughput measurements. */
+int epic_b200_field_set_tracking(epic_b200_field *f, int on);
 
 /* Device address of global layer `layer` in the buffer that currently holds the field (it changes
  * with every pass: query after each run).  Null when the layer is not held by this slab. */

@@ -21,8 +21,11 @@ pytestmark = pytest.mark.gpu
 class LocalGroup:
     """Drives `world` slabs that live in this process; halo exchange = device-to-device copies."""
 
-    def __init__(self, shape, world, math="strict", p2p=False):
+    def __init__(self, shape, world, math="strict", p2p=False, tracking=False):
         self.slabs = [GpuSlab(shape, r, world, math=math) for r in range(world)]
+        if tracking:    # static-tile skipping, as ShardedSolver.solve switches it on
+            for s in self.slabs:
+                s.set_tracking(True)
         self.world = world
         self.iteration = 0
         self.delta = 0.0
@@ -74,12 +77,15 @@ class LocalGroup:
         return np.concatenate([s.download_owned() for s in self.slabs], 0)
 
 
+@pytest.mark.parametrize("tracking", [False, True])
 @pytest.mark.parametrize("p2p", [False, True])
 @pytest.mark.parametrize("world,case", [(2, "random_ragged"), (3, "random256"), (5, "proc_maze"), (2, "random3d_ragged"),
                                         (3, "random48x3")])
-def test_slabs_on_one_gpu_bit_identical(golden, libepic_built, world, case, p2p):
+def test_slabs_on_one_gpu_bit_identical(golden, libepic_built, world, case, p2p, tracking):
     u, locked, eps, stagger = common.case_input(case)
-    grp = LocalGroup(u.shape, world, p2p=p2p)
+    if tracking and u.ndim == 3:
+        pytest.skip("static-tile skipping is a 2-D feature")
+    grp = LocalGroup(u.shape, world, p2p=p2p, tracking=tracking)
     grp.upload(u, locked)
     done = 0
     for k in sorted(int(c) for c in golden[case]["checkpoints"]):
@@ -115,3 +121,27 @@ def test_nccl_two_ranks_bit_identical(golden, libepic_built, tmp_path):
         assert res["halo"] == halo
         assert res["iterations"] == g["iterations"] and res["delta_hex"] == g["delta_hex"]
         assert res["sha1_u"] == g["sha1_u"], "%s over %s differs from the reference" % (case, halo)
+
+
+@pytest.mark.parametrize("p2p", [False, True])
+def test_sharded_solve_with_static_tile_skipping_equals_one_field(libepic_built, p2p):
+    """Solve to epsilon on three slabs with static-tile skipping on (edge tiles always run): iteration count,
+    delta and field must equal the single-field solve (itself pinned to the golden vectors), and interior
+    tiles must actually have been skipped."""
+    from epic_b200.field import Field
+    shape = (1500, 1024)
+    u, locked = grids.random_obstacles(shape, 0.2, 3, seed=31)
+    f = Field(shape)
+    f.upload(u, locked)
+    it1, d1 = f.solve(1e-3, 100)
+    want = common.sha1(f.download_u())
+    f.close()
+    grp = LocalGroup(shape, 3, p2p=p2p, tracking=True)
+    grp.upload(u, locked)
+    while True:
+        grp.run((-grp.iteration) % 100 + 1, True)
+        if grp.delta < 1e-3 and grp.iteration >= max(shape):
+            break
+    assert (grp.iteration, grp.delta) == (it1, d1)
+    assert common.sha1(grp.field()) == want
+    assert sum(s.field.info()["skipped_tiles"] for s in grp.slabs) > 0

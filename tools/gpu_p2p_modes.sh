@@ -5,7 +5,7 @@ N=${1:-2}; STEPS=${2:-5}
 mkdir -p gpurun_out
 for mode in kernel stream kernel stream; do
   EPIC_P2P_SYNC=$mode timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2971$N \
-      bench.py --gpus $N --steps $STEPS --warmup 3 --no-cpu > gpurun_out/p2p_${mode}_n$N.json 2> gpurun_out/p2p_${mode}_n$N.err
+      bench.py --gpus $N --steps $STEPS --warmup 3 --no-cpu --no-tte > gpurun_out/p2p_${mode}_n$N.json 2> gpurun_out/p2p_${mode}_n$N.err
   python - <<PY
 import json
 try:
