@@ -92,6 +92,20 @@ bool allow_smem(K kernel, size_t bytes)
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) == cudaSuccess;
 }
 
+template <class Math, int NT>
+bool allow_smem_modes()
+{
+    return allow_smem(sweep2d_kernel<Math, NT, kPlain>, 227 * 1024) && allow_smem(sweep2d_kernel<Math, NT, kTrack>, 227 * 1024) &&
+           allow_smem(sweep2d_kernel<Math, NT, kP2P>, 227 * 1024) &&
+           allow_smem(sweep2d_kernel<Math, NT, kTrack | kP2P>, 227 * 1024);
+}
+
+bool allow_smem_2d()
+{
+    return allow_smem_modes<StrictMath, 256>() && allow_smem_modes<StrictMath, 512>() && allow_smem_modes<FastMath, 256>() &&
+           allow_smem_modes<FastMath, 512>();
+}
+
 }  // namespace
 
 FieldConfig config_from_env()
@@ -211,14 +225,7 @@ int Field::create(Field **out, unsigned n, const uint64_t *gm, uint64_t row0, ui
         // to hide wave effects (tools/sweep_timing.py, profiles/r01c_tile_candidates.md).  Small grids
         // end up with small tiles (every SM gets work, short passes), slabs of a sharded grid with a
         // tile height that fills the last wave.
-        if (!allow_smem(sweep2d_kernel<StrictMath, 256>, 227 * 1024) ||
-            !allow_smem(sweep2d_kernel<FastMath, 256>, 227 * 1024) ||
-            !allow_smem(sweep2d_kernel<StrictMath, 512>, 227 * 1024) ||
-            !allow_smem(sweep2d_kernel<FastMath, 512>, 227 * 1024) ||
-            !allow_smem(sweep2d_kernel<StrictMath, 256, true>, 227 * 1024) ||
-            !allow_smem(sweep2d_kernel<FastMath, 256, true>, 227 * 1024) ||
-            !allow_smem(sweep2d_kernel<StrictMath, 512, true>, 227 * 1024) ||
-            !allow_smem(sweep2d_kernel<FastMath, 512, true>, 227 * 1024)) {
+        if (!allow_smem_2d()) {
             cudaGetLastError();
             delete f;
             return kInvalidCudaParam;
@@ -752,14 +759,7 @@ int Field::launch_pass_2d(uint32_t it0, uint32_t count, bool check_last)
     }
 
     if (!attr_done_) {  // per device, so per field
-        if (!allow_smem(sweep2d_kernel<StrictMath, 256>, 227 * 1024) ||
-            !allow_smem(sweep2d_kernel<FastMath, 256>, 227 * 1024) ||
-            !allow_smem(sweep2d_kernel<StrictMath, 512>, 227 * 1024) ||
-            !allow_smem(sweep2d_kernel<FastMath, 512>, 227 * 1024) ||
-            !allow_smem(sweep2d_kernel<StrictMath, 256, true>, 227 * 1024) ||
-            !allow_smem(sweep2d_kernel<FastMath, 256, true>, 227 * 1024) ||
-            !allow_smem(sweep2d_kernel<StrictMath, 512, true>, 227 * 1024) ||
-            !allow_smem(sweep2d_kernel<FastMath, 512, true>, 227 * 1024)) {
+        if (!allow_smem_2d()) {
             cudaGetLastError();
             return kInvalidCudaParam;
         }
@@ -783,27 +783,35 @@ int Field::launch_pass_2d(uint32_t it0, uint32_t count, bool check_last)
     } else {
         chg_stale_ = true;
     }
+    const int mode = (track ? kTrack : kPlain) | (kernel_sync ? kP2P : kPlain);
+#define EPIC_LAUNCH_2D(MATH, NT, MODE) \
+    sweep2d_kernel<MATH, NT, MODE><<<grid, NT, smem, stream_>>>(tmap_[cur_], p, m)
+#define EPIC_LAUNCH_2D_MODES(MATH, NT)                                   \
+    switch (mode) {                                                      \
+    case kPlain: EPIC_LAUNCH_2D(MATH, NT, kPlain); break;                \
+    case kTrack: EPIC_LAUNCH_2D(MATH, NT, kTrack); break;                \
+    case kP2P: EPIC_LAUNCH_2D(MATH, NT, kP2P); break;                    \
+    default: EPIC_LAUNCH_2D(MATH, NT, kTrack | kP2P); break;             \
+    }
     if (cfg_.math == MATH_STRICT) {
         StrictMath m;
         m.init(kLog4);
         if (NT_ == 512) {
-            if (track) sweep2d_kernel<StrictMath, 512, true><<<grid, 512, smem, stream_>>>(tmap_[cur_], p, m);
-            else sweep2d_kernel<StrictMath, 512><<<grid, 512, smem, stream_>>>(tmap_[cur_], p, m);
+            EPIC_LAUNCH_2D_MODES(StrictMath, 512)
         } else {
-            if (track) sweep2d_kernel<StrictMath, 256, true><<<grid, 256, smem, stream_>>>(tmap_[cur_], p, m);
-            else sweep2d_kernel<StrictMath, 256><<<grid, 256, smem, stream_>>>(tmap_[cur_], p, m);
+            EPIC_LAUNCH_2D_MODES(StrictMath, 256)
         }
     } else {
         FastMath m;
         m.ln2n = 1.3862943611198906f;
         if (NT_ == 512) {
-            if (track) sweep2d_kernel<FastMath, 512, true><<<grid, 512, smem, stream_>>>(tmap_[cur_], p, m);
-            else sweep2d_kernel<FastMath, 512><<<grid, 512, smem, stream_>>>(tmap_[cur_], p, m);
+            EPIC_LAUNCH_2D_MODES(FastMath, 512)
         } else {
-            if (track) sweep2d_kernel<FastMath, 256, true><<<grid, 256, smem, stream_>>>(tmap_[cur_], p, m);
-            else sweep2d_kernel<FastMath, 256><<<grid, 256, smem, stream_>>>(tmap_[cur_], p, m);
+            EPIC_LAUNCH_2D_MODES(FastMath, 256)
         }
     }
+#undef EPIC_LAUNCH_2D_MODES
+#undef EPIC_LAUNCH_2D
     if (track && count < 2) {
         // a pass of one half-sweep has only exercised one colour: its "nothing changed" proves nothing
         // about the other one, so the next pass must not skip on these flags

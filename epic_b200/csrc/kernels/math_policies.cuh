@@ -52,15 +52,18 @@ __device__ __forceinline__ void load_math_tables(MathTables *t, int tid, int nth
     }
 }
 
-struct StrictMath {
-    const MathTables *t;
+struct alignas(16) StrictMath {
     // Every double constant lives in the kernel-parameter (constant) bank, where DFMA/DADD read it as
-    // an operand; as literals they would be re-materialised with two moves per use.
+    // an operand through uniform registers; as literals they would be re-materialised with two moves per
+    // use.  The struct is 16-byte aligned with the doubles first so that pairs of them load with one
+    // LDCU.128: when a longer Sweep2DParams once shifted them to 8 (mod 16), ptxas fell back to per-use
+    // LDC.64 into vector registers and the strict sweep lost 6 %.
     double log2n;      // glibc log(2.0 * n)
     double inv_ln2n;   // kExpInvLn2N
     double shift;      // kExpShift
     double c0, c1, c2; // kExpC0..2
     double ln2, a0, a1, a2;
+    const MathTables *t;
 
     __host__ __device__ void init(double log_2n)
     {

@@ -272,14 +272,22 @@ struct RowCtx {
     }
 };
 
-template <class Math, int NT, bool TRACK = false>
+// MODE: bit 0 = static-tile skipping (kTrack), bit 1 = in-kernel ordering of passes between GPUs (kP2P).
+// Compile-time, because either costs registers that the plain single-slab kernel cannot spare (the strict
+// variant runs at its 64-register cap: carrying the P2P state through the row loop cost it 6 %).
+enum { kPlain = 0, kTrack = 1, kP2P = 2 };
+
+template <class Math, int NT, int MODE = kPlain>
 __global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1))
-sweep2d_kernel(const __grid_constant__ CUtensorMap src_map, const Sweep2DParams p, const Math math_in)
+sweep2d_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ Sweep2DParams p,
+               const __grid_constant__ Math math_in)
 {
+    constexpr bool TRACK = (MODE & kTrack) != 0;
+    constexpr bool P2P = (MODE & kP2P) != 0;
     if (*p.ctrl_done) {
         return;  // a previous check sweep already met the termination rule
     }
-    const bool p2p = p.p2p_sync != 0;
+    constexpr bool p2p = P2P;
     const int tx = blockIdx.x % p.ntx, ty = tile_row_of(blockIdx.x / p.ntx, (int)p.nty, p2p);
     const int by0 = (int)p.own_lo + ty * (int)p.out_h - (int)p.T;  // buffer row of tile row 0
     if (TRACK) {
@@ -320,22 +328,22 @@ sweep2d_kernel(const __grid_constant__ CUtensorMap src_map, const Sweep2DParams 
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int gx0 = tx * (int)p.out_w - (int)p.HC;                 // grid column of tile column 0
     // does this tile read the ghost rows of / store into a neighbour?
-    const bool edge_up = p2p && p.signal_up != nullptr && by0 < (int)p.own_lo;
-    const bool edge_dn = p2p && p.signal_dn != nullptr && by0 + (int)p.TH > (int)p.own_hi;
+    const bool edge_up = P2P && p.signal_up != nullptr && by0 < (int)p.own_lo;
+    const bool edge_dn = P2P && p.signal_dn != nullptr && by0 + (int)p.TH > (int)p.own_hi;
 
     if (tid == 0) {
         mbar_init(bar, 1);
-        if (edge_up) {
+        if (P2P && edge_up) {
             while (ld_acquire_sys(p.wait_up) + 1u < p.pass_index) {
                 __nanosleep(64);
             }
         }
-        if (edge_dn) {
+        if (P2P && edge_dn) {
             while (ld_acquire_sys(p.wait_dn) + 1u < p.pass_index) {
                 __nanosleep(64);
             }
         }
-        if (edge_up || edge_dn) {
+        if (P2P && (edge_up || edge_dn)) {
             // the ghost rows were written by another GPU's generic-proxy stores; the tile load below reads
             // them through the async proxy
             asm volatile("fence.proxy.async;" ::: "memory");
@@ -464,7 +472,7 @@ sweep2d_kernel(const __grid_constant__ CUtensorMap src_map, const Sweep2DParams 
         }
     }
 
-    if (edge_up || edge_dn) {
+    if (P2P && (edge_up || edge_dn)) {
         __threadfence_system();     // this thread's stores into the neighbour are visible system-wide ...
         __syncthreads();            // ... for every thread of the CTA before thread 0 counts the tile as done
         if (tid == 0) {
