@@ -136,6 +136,39 @@ struct Rows3D {
         b = nw;
     }
 
+    // Exactly n = 2 or 4 rows from r0, fully unrolled with the colour of each row fixed at compile time: with
+    // the default tile height every warp's share of a layer is such a group, and the generic loop below
+    // (peel, pair loop, tail) costs about as many instructions as a row of arithmetic.
+    template <bool CHECK>
+    __device__ __forceinline__ void band4(float *pc, const float *pm, const float *pp, const uint8_t *mk, int r0, int n,
+                                          uint32_t par, bool chk, int chk_lo, int chk_hi)
+    {
+        float4 a = ld(pc, r0 - 1, lane), b = ld(pc, r0, lane), c = ld(pc, r0 + 1, lane);
+        const bool k0 = chk && r0 >= chk_lo && r0 < chk_hi, k1 = chk && r0 + 1 >= chk_lo && r0 + 1 < chk_hi;
+        const bool k2 = chk && r0 + 2 >= chk_lo && r0 + 2 < chk_hi, k3 = chk && r0 + 3 >= chk_lo && r0 + 3 < chk_hi;
+        if (((par + (uint32_t)r0) & 1u) == 0u) {
+            row<true, CHECK>(pc, pm, pp, mk, r0, a, b, c, k0);
+            a = ld(pc, r0 + 2, lane);
+            row<false, CHECK>(pc, pm, pp, mk, r0 + 1, b, c, a, k1);
+            if (n > 2) {
+                b = ld(pc, r0 + 3, lane);
+                row<true, CHECK>(pc, pm, pp, mk, r0 + 2, c, a, b, k2);
+                c = ld(pc, r0 + 4, lane);
+                row<false, CHECK>(pc, pm, pp, mk, r0 + 3, a, b, c, k3);
+            }
+        } else {
+            row<false, CHECK>(pc, pm, pp, mk, r0, a, b, c, k0);
+            a = ld(pc, r0 + 2, lane);
+            row<true, CHECK>(pc, pm, pp, mk, r0 + 1, b, c, a, k1);
+            if (n > 2) {
+                b = ld(pc, r0 + 3, lane);
+                row<false, CHECK>(pc, pm, pp, mk, r0 + 2, c, a, b, k2);
+                c = ld(pc, r0 + 4, lane);
+                row<true, CHECK>(pc, pm, pp, mk, r0 + 3, a, b, c, k3);
+            }
+        }
+    }
+
     // Rows [ra, rb) of one layer.  par = (it + x0 + x1 of tile row 0) & 1: cell (r, c) is active when
     // (par + r + c) is even.  chk_lo / chk_hi: rows whose deltas count (the output rows), for lanes with chk.
     template <bool CHECK>
@@ -143,6 +176,10 @@ struct Rows3D {
                                          uint32_t par, bool chk, int chk_lo, int chk_hi)
     {
         if (ra >= rb) {
+            return;
+        }
+        if (rb - ra == 4 || rb - ra == 2) {
+            band4<CHECK>(pc, pm, pp, mk, ra, rb - ra, par, chk, chk_lo, chk_hi);
             return;
         }
         float4 a = ld(pc, ra - 1, lane), b = ld(pc, ra, lane), c;
