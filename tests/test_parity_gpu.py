@@ -381,3 +381,19 @@ def test_static_tile_skipping_is_bit_identical_and_active(libepic_built, monkeyp
     assert out["0"][:3] == out["1"][:3] and out["0"][4:7] == out["1"][4:7]
     assert out["0"][3] == 0 and out["0"][7] == 0
     assert out["1"][3] > 0 and out["1"][7] > out["1"][3]
+
+
+@pytest.mark.parametrize("sweeps_per_pass,tile_rows,threads", [
+    (1, 16, 256), (2, 24, 256), (3, 32, 512), (4, 16, 256), (4, 40, 256), (4, 96, 512), (4, 64, 512), (5, 48, 256),
+    (6, 56, 512), (8, 32, 256), (8, 96, 512)])
+def test_every_tile_geometry_gives_the_same_bits(golden, libepic_built, monkeypatch, sweeps_per_pass, tile_rows, threads):
+    """The cost model picks (threads, tile rows) from the grid size and T defaults to 4; every other legal
+    geometry -- halo depth 1..8, 16..96 tile rows, 8 or 16 warps -- must produce the golden fields too:
+    a ragged random grid call by call, and a procedural maze solved to epsilon (with static-tile skipping)."""
+    monkeypatch.setenv("EPIC_SWEEPS_PER_PASS", str(sweeps_per_pass))
+    monkeypatch.setenv("EPIC_TILE_ROWS", str(tile_rows))
+    monkeypatch.setenv("EPIC_THREADS", str(threads))
+    s = common.check_checkpoints(make_gpu, "random_ragged", golden["random_ragged"])
+    s.close()
+    s = common.check_complete(make_gpu, "proc_maze", golden["proc_maze"])
+    s.close()
