@@ -224,4 +224,41 @@ EPIC_HD float strict_logf_sum(float x, const Table &tab)
     return (float)strict_fma(y, r, y0);
 }
 
+// The 2-D update as the reference writes it (harmonic_cpu.cpp:58-70): max of the four neighbours, four
+// expf, three float adds left to right, logf, the float add of the maximum and the subtraction of log(4.0)
+// in double.  `e` / `l` are the expf / logf to use.
+template <typename Exp, typename Log>
+EPIC_HD float strict_update4_reference(float a, float b, float c, float d, Exp e, Log l)
+{
+    float mx = (a < b) ? b : a;
+    mx = (mx < c) ? c : mx;
+    mx = (mx < d) ? d : mx;
+    float s = e(a - mx) + e(b - mx);
+    s = s + e(c - mx);
+    s = s + e(d - mx);
+    const float t1 = mx + l(s);
+    return (float)((double)t1 - kLog4);
+}
+
+// The same value with three expf: the form of StrictMath::update4 (math_policies.cuh).  The largest
+// neighbour's term is expf(0) = 1; a min/max network finds the three losers; E(a) + E(b) is commutative, so
+// only the (c, d) pair needs its order restored.
+template <typename Exp, typename Log>
+EPIC_HD float strict_update4_network(float a, float b, float c, float d, Exp e, Log l)
+{
+    const float hi1 = (a < b) ? b : a, lo1 = (a < b) ? a : b;
+    const float hi2 = (c < d) ? d : c, lo2 = (c < d) ? c : d;
+    const float mx = (hi1 < hi2) ? hi2 : hi1, mid = (hi1 < hi2) ? hi1 : hi2;
+    const float e1 = e(lo1 - mx), e2 = e(lo2 - mx), em = e(mid - mx);
+    const bool p = hi1 < hi2;
+    const float eh1 = p ? em : 1.0f, eh2 = p ? 1.0f : em;
+    const bool q = c < d;
+    const float ec = q ? e2 : eh2, ed = q ? eh2 : e2;
+    float s = eh1 + e1;
+    s = s + ec;
+    s = s + ed;
+    const float t1 = mx + l(s);
+    return (float)((double)t1 - kLog4);
+}
+
 }  // namespace epic_b200

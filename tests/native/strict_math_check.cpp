@@ -51,6 +51,38 @@ int main(int argc, char **argv)
             bad_l++;
         }
     }
-    printf("expf mismatches %llu of %llu\nlogf mismatches %llu of %llu\n", bad_e, n_e, bad_l, n_l);
-    return (bad_e || bad_l) ? 1 : 0;
+    // the three-expf form of the 2-D update (StrictMath::update4) against the reference's four-expf form, both
+    // on the host libm: random neighbourhoods drawn from the values a field holds (relaxed potentials, the
+    // -1e6 of obstacles and unreached cells, goals at 0), with ties, signed zeros and near-ties forced in
+    unsigned long long bad_u = 0, n_u = 0;
+    {
+        auto e = [](float x) { return expf(x); };
+        auto l = [](float x) { return logf(x); };
+        uint64_t st = 0x9e3779b97f4a7c15ull;
+        auto rnd = [&st]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return st; };
+        const float special[8] = {0.0f, -0.0f, -1e6f, -1e6f, -0x1p-149f, -104.25f, -3.5f, -969.5537f};
+        for (unsigned long long it = 0; it < 40000000ull / stride; ++it) {
+            float v[4];
+            const float base = -(float)(rnd() % 2000) * 0.5f;
+            for (int i = 0; i < 4; ++i) {
+                const uint64_t r = rnd();
+                switch (r & 7) {
+                case 0: v[i] = special[(r >> 3) & 7]; break;
+                case 1: v[i] = base; break;                                            // exact tie with the base
+                case 2: v[i] = strict_from_fbits(strict_fbits(base) + (uint32_t)((r >> 3) & 3)); break;  // a few ulps off
+                default: v[i] = base - (float)((r >> 8) & 0xffff) * (1.0f / 4096.0f) * (float)(1 + ((r >> 3) & 15)); break;
+                }
+            }
+            const float want = strict_update4_reference(v[0], v[1], v[2], v[3], e, l);
+            const float got = strict_update4_network(v[0], v[1], v[2], v[3], e, l);
+            n_u++;
+            if (strict_fbits(want) != strict_fbits(got) && !(want != want && got != got)) {
+                if (bad_u < 5) printf("update4(%a, %a, %a, %a): got %a want %a\n", v[0], v[1], v[2], v[3], got, want);
+                bad_u++;
+            }
+        }
+    }
+    printf("expf mismatches %llu of %llu\nlogf mismatches %llu of %llu\nupdate4 mismatches %llu of %llu\n", bad_e, n_e, bad_l,
+           n_l, bad_u, n_u);
+    return (bad_e || bad_l || bad_u) ? 1 : 0;
 }

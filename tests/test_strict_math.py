@@ -15,3 +15,4 @@ def test_strict_math_header_equals_host_libm_exhaustively(tmp_path):
     r = subprocess.run([exe, "1"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout
     assert "expf mismatches 0 of 2139095041" in r.stdout and "logf mismatches 0 of" in r.stdout
+    assert "update4 mismatches 0 of 40000000" in r.stdout
