@@ -222,7 +222,7 @@ int Field::create(Field **out, unsigned n, const uint64_t *gm, uint64_t row0, ui
         // Tile geometry: estimate the time of one pass for every candidate (threads, tile rows) and keep
         // the cheapest.  A tile costs its output rows over `eff`; an SM works through its tiles k at a time (k =
         // resident CTAs); `eff` is the measured relative speed of the candidate on a grid large enough
-        // to hide wave effects (tools/sweep_timing.py, profiles/r01c_tile_candidates.md).  Small grids
+        // to hide wave effects (tools/sweep_timing.py, profiles/r01i_tile_candidates.txt).  Small grids
         // end up with small tiles (every SM gets work, short passes), slabs of a sharded grid with a
         // tile height that fills the last wave.
         if (!allow_smem_2d()) {
@@ -232,10 +232,10 @@ int Field::create(Field **out, unsigned n, const uint64_t *gm, uint64_t row0, ui
         }
         f->attr_done_ = true;
         struct Cand { int nt, th; float eff_strict, eff_fast; };
-        static const Cand cands[] = {{512, 96, 1.00f, 0.98f}, {512, 88, 0.99f, 0.96f}, {512, 80, 0.977f, 0.94f},
-                                     {512, 72, 0.96f, 0.97f}, {512, 64, 0.95f, 1.00f}, {256, 64, 0.915f, 0.985f},
-                                     {256, 56, 0.89f, 0.99f}, {256, 48, 0.874f, 0.997f}, {256, 40, 0.84f, 0.98f},
-                                     {256, 32, 0.805f, 0.97f}, {256, 24, 0.70f, 0.85f}, {256, 16, 0.50f, 0.60f}};
+        static const Cand cands[] = {{512, 96, 1.000f, 0.952f}, {512, 88, 0.987f, 0.936f}, {512, 80, 0.974f, 0.919f},
+                                     {512, 72, 0.962f, 0.902f}, {512, 64, 0.949f, 0.978f}, {256, 64, 0.930f, 0.971f},
+                                     {256, 56, 0.914f, 0.948f}, {256, 48, 0.885f, 0.996f}, {256, 40, 0.849f, 1.000f},
+                                     {256, 32, 0.814f, 0.981f}, {256, 24, 0.717f, 0.865f}, {256, 16, 0.50f, 0.60f}};
         const int HC = 4 * ((f->T_ + 3) / 4);
         const int out_w = kTileW - 2 * HC;
         const uint64_t ntx = (gm[1] + out_w - 1) / out_w;
