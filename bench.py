@@ -133,24 +133,31 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
+def grid_shape(args):
+    return (args.size,) * args.dims
+
+
 def workload(args):
-    return {"workload": "synthetic %dx%d random-obstacle grid (p=0.2, 64 goals, seed 1234), row-slab sharded"
-                        % (args.size, args.size),
-            "grid": [args.size, args.size], "epsilon": 1e-3, "stagger": SWEEPS_PER_STEP,
-            "sweeps_per_step": SWEEPS_PER_STEP, "updates_per_step": args.size * args.size // 2 * SWEEPS_PER_STEP,
-            "parallelism": "row-slab x%d" % args.gpus, "halo": (args.halo if args.gpus > 1 else None),
-            "l2": "grid (%.2f GiB per buffer) is larger than L2; no flush needed" % (args.size * args.size * 4 / 2**30)}
+    shape = grid_shape(args)
+    cells = int(np.prod(shape, dtype=np.int64))
+    return {"workload": "synthetic %s random-obstacle grid (p=0.2, 64 goals, seed 1234), %s-slab sharded"
+                        % ("x".join(str(s) for s in shape), "row" if args.dims == 2 else "x0"),
+            "grid": list(shape), "epsilon": 1e-3, "stagger": SWEEPS_PER_STEP,
+            "sweeps_per_step": SWEEPS_PER_STEP, "updates_per_step": cells // 2 * SWEEPS_PER_STEP,
+            "parallelism": "%s-slab x%d" % ("row" if args.dims == 2 else "x0", args.gpus),
+            "halo": (args.halo if args.gpus > 1 else None),
+            "l2": "grid (%.2f GiB per buffer) is larger than L2; no flush needed" % (cells * 4 / 2**30)}
 
 
 # ---------------------------------------------------------------------------------------------------
 # reference arm: the reference's own CPU code on the host cores
 
-def cpu_reference_rate(size, rows, sweeps, warmup=0):
-    """(updates/s, description) of the reference CPU half-sweep over a `rows` x `size` band."""
+def cpu_reference_rate(size, rows, sweeps, warmup=0, dims=2):
+    """(updates/s, description) of the reference CPU half-sweep over the first `rows` x0-layers of the grid."""
     from epic_b200 import grids
     from oracle import oracle as orc
-    u, locked = grids.random_obstacles((size, size), 0.2, 64, seed=1234, row0=0, rows=rows)
-    locked[-1, :] = 1
+    u, locked = grids.random_obstacles((size,) * dims, 0.2, 64, seed=1234, row0=0, rows=rows)
+    locked[-1] = 1
     if orc.have_ref():
         solver, kind, cores = orc.Reference(u, locked, 1e-3, SWEEPS_PER_STEP), "reference", 1
         what = "harmonic_update_cpu of the untouched reference sources (oracle/_ref), serial as shipped"
@@ -165,7 +172,7 @@ def cpu_reference_rate(size, rows, sweeps, warmup=0):
     for _ in range(sweeps):
         solver.update()
     dt = time.perf_counter() - t0
-    updates = (rows - 2) * (size - 2) / 2.0 * sweeps
+    updates = (rows - 2) * float(size - 2) ** (dims - 1) / 2.0 * sweeps
     return updates / dt, dt, kind, cores, what
 
 
@@ -175,11 +182,11 @@ def run_reference(args):
         return
     # one step = one half-sweep over a band sized so that the whole run stays within ~150 s at ~25 M updates/s
     budget_updates = 150.0 * 25e6 / max(1, args.steps + args.warmup)
-    rows = int(min(args.size, max(64, budget_updates / (args.size / 2.0))))
-    rate, dt, kind, cores, what = cpu_reference_rate(args.size, rows, args.steps, args.warmup)
+    rows = int(min(args.size, max(8, budget_updates / (float(args.size) ** (args.dims - 1) / 2.0))))
+    rate, dt, kind, cores, what = cpu_reference_rate(args.size, rows, args.steps, args.warmup, args.dims)
     value = rate / 1e9
-    sample = "%d half-sweeps (steps) over rows 0..%d of the %dx%d grid; %s" % (args.steps, rows - 1, args.size,
-                                                                             args.size, what)
+    sample = "%d half-sweeps (steps) over x0 = 0..%d of the %s grid; %s" % (
+        args.steps, rows - 1, "x".join(str(v) for v in grid_shape(args)), what)
     line = {"impl": "reference", "metric": "Gcell-updates/s", "value": value, "unit": "Gcell-updates/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -213,14 +220,15 @@ def run_native(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = libepic.load()
     size = args.size
-    shape = (size, size)
-    updates_per_step = size * size // 2 * SWEEPS_PER_STEP
+    shape = grid_shape(args)
+    layer_cells = size ** (args.dims - 1)
+    updates_per_step = size * layer_cells // 2 * SWEEPS_PER_STEP
 
     # what this rank holds (owned rows + ghost rows), generated once and kept in pinned host memory: the
     # e2e leg moves it inside the timed region
     from epic_b200.sharded import partition as _partition
     row0, nrows = _partition(size, world, rank)
-    ghost = 4 if world > 1 else 0
+    ghost = (4 if args.dims == 2 else 2) if world > 1 else 0
     lo, hi = max(0, row0 - ghost), min(size, row0 + nrows + ghost)
     u_held, locked_held = grids.random_obstacles(shape, 0.2, 64, seed=1234, row0=lo, rows=hi - lo)
     u_pin = torch.from_numpy(u_held).pin_memory()
@@ -281,11 +289,11 @@ def run_native(args):
         stop.record()
         torch.cuda.synchronize()
         kern_ms = start.elapsed_time(stop) / passes
-        own_updates_per_pass = slab.rows * size // 2 * info["sweeps_per_pass"]
+        own_updates_per_pass = slab.rows * layer_cells // 2 * info["sweeps_per_pass"]
         achieved = own_updates_per_pass * ALGO_BYTES_PER_UPDATE / (kern_ms * 1e-3) / 1e9
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-        if os.path.exists(tpath) and size == 16384:
+        if os.path.exists(tpath) and size == 16384 and args.dims == 2:
             with open(tpath) as f:
                 traffic = json.load(f).get(math)
                 traffic = traffic / world if traffic else None
@@ -308,7 +316,7 @@ def run_native(args):
                 h.run_iterations(SWEEPS_PER_STEP, "gpu")
                 h.get_potential_values_gpu()
         else:
-            out_pin = torch.empty((slab.rows, size), dtype=torch.float32).pin_memory()
+            out_pin = torch.empty((slab.rows,) + shape[1:], dtype=torch.float32).pin_memory()
             h2d = u_host.nbytes + l_host.nbytes
             d2h = out_pin.numel() * 4
 
@@ -382,7 +390,7 @@ def run_native(args):
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "achieved": achieved * world, "peak": peak * world, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                             "kernel": "sweep2d_kernel<%s>" % ("StrictMath" if math == "strict" else "FastMath"),
+                             "kernel": "sweep%dd_kernel<%s>" % (args.dims, "StrictMath" if math == "strict" else "FastMath"),
                              "kernel_ms": kern_ms, "algorithmic_bytes_per_update": ALGO_BYTES_PER_UPDATE,
                              "updates_per_launch": own_updates_per_pass},
                 "time_to_epsilon": tte, "delta_after_timed_steps": delta_after}
@@ -394,9 +402,11 @@ def run_native(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        rate, dt, kind, cores, what = cpu_reference_rate(size, size, 4)
+        cpu_rows = size if args.dims == 2 else min(size, 256)
+        rate, dt, kind, cores, what = cpu_reference_rate(size, cpu_rows, 4, dims=args.dims)
         cpu = {"value": rate / 1e9, "unit": "Gcell-updates/s", "cores": cores, "kind": kind, "host_cores": os.cpu_count(),
-               "sample": "4 half-sweeps of the full %dx%d grid (%.1f s); %s" % (size, size, dt, what)}
+               "sample": "4 half-sweeps of x0 = 0..%d of the %s grid (%.1f s); %s" % (
+                   cpu_rows - 1, "x".join(str(v) for v in shape), dt, what)}
 
     if rank == 0:
         line = {"metric": "Gcell-updates/s", "value": main_res["value"], "unit": "Gcell-updates/s", "n_gpus": world,
@@ -423,7 +433,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["native", "reference"], default="native")
-    ap.add_argument("--size", type=int, default=16384)
+    ap.add_argument("--size", type=int, default=16384, help="cells per dimension")
+    ap.add_argument("--dims", type=int, choices=[2, 3], default=2,
+                    help="2: BASELINE.json config 3 (size^2, the default and the headline); 3: config 5 (use --size 1024)")
     ap.add_argument("--math", choices=["strict", "fast"], default=os.environ.get("EPIC_MATH", "strict"))
     ap.add_argument("--tte", action="store_true", default=True,
                     help="also run to epsilon and report the time (default; twice: every tile swept / static tiles skipped)")
