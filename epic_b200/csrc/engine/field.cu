@@ -198,7 +198,8 @@ int Field::create(Field **out, unsigned n, const uint64_t *gm, uint64_t row0, ui
         }
         f->NT_ = k3Threads;
         const size_t smem = sweep3d_smem_bytes((uint32_t)f->TH_);
-        if (!allow_smem(sweep3d_kernel<StrictMath>, smem) || !allow_smem(sweep3d_kernel<FastMath>, smem)) {
+        if (!allow_smem(sweep3d_kernel<StrictMath>, smem) || !allow_smem(sweep3d_kernel<FastMath>, smem) ||
+            !allow_smem(sweep3d_kernel<StrictMath, true>, smem) || !allow_smem(sweep3d_kernel<FastMath, true>, smem)) {
             cudaGetLastError();
             delete f;
             return kInvalidCudaParam;
@@ -216,6 +217,28 @@ int Field::create(Field **out, unsigned n, const uint64_t *gm, uint64_t row0, ui
         if (gm[1] * f->pitch_ >= 0x80000000ull) {
             delete f;
             return kInvalidData;   // the 3-D kernel addresses a layer with 32-bit offsets
+        }
+        // Layers per CTA: a CTA costs (its layers + the 2 * 2 halo layers); the grid runs in waves of
+        // ctas_per_sm_ CTAs per SM.  Take the split along x0 with the cheapest estimated pass.
+        {
+            const uint64_t ntx3 = (gm[2] + k3OutW - 1) / k3OutW;
+            const uint64_t nty3 = (gm[1] + (f->TH_ - 2 * k3HR) - 1) / (f->TH_ - 2 * k3HR);
+            const uint64_t tiles_xy = ntx3 * nty3;
+            const uint64_t slots = (uint64_t)f->ctas_per_sm_ * (uint64_t)f->sms_;
+            uint64_t best_cost = 0;
+            uint32_t best_chunk = (uint32_t)rows;
+            const uint64_t max_ntz = std::max<uint64_t>(1, std::min<uint64_t>(256, rows / 4));
+            for (uint64_t ntz = 1; ntz <= max_ntz; ++ntz) {
+                const uint64_t chunk = (rows + ntz - 1) / ntz;
+                const uint64_t ctas = tiles_xy * ((rows + chunk - 1) / chunk);
+                const uint64_t cost = ((ctas + slots - 1) / slots) * (chunk + 2 * k3HR + 2);
+                if (best_cost == 0 || cost < best_cost) {
+                    best_cost = cost;
+                    best_chunk = (uint32_t)chunk;
+                }
+            }
+            f->zchunk_ = best_chunk;
+            f->chg_bytes_ = (size_t)round_up(tiles_xy * ((rows + best_chunk - 1) / best_chunk), 256);
         }
     }
     if (n == 2) {
@@ -293,11 +316,13 @@ int Field::create(Field **out, unsigned n, const uint64_t *gm, uint64_t row0, ui
     ok = ok && cudaMalloc(&f->freemask_, mbytes) == cudaSuccess && cudaMemset(f->freemask_, 0, mbytes) == cudaSuccess;
     ok = ok && cudaMalloc(&f->ctrl_, sizeof(Ctrl)) == cudaSuccess && cudaMemset(f->ctrl_, 0, sizeof(Ctrl)) == cudaSuccess;
     ok = ok && cudaMalloc(&f->flags_, 256) == cudaSuccess && cudaMemset(f->flags_, 0, 256) == cudaSuccess;
-    if (n == 2) {
-        const int HC = 4 * ((f->T_ + 3) / 4);
-        const uint64_t ntx = (gm[1] + (kTileW - 2 * HC) - 1) / (kTileW - 2 * HC);
-        const uint64_t nty = (rows + (f->TH_ - 2 * f->T_) - 1) / (f->TH_ - 2 * f->T_);
-        f->chg_bytes_ = (size_t)round_up(ntx * nty, 256);
+    {
+        if (n == 2) {
+            const int HC = 4 * ((f->T_ + 3) / 4);
+            const uint64_t ntx = (gm[1] + (kTileW - 2 * HC) - 1) / (kTileW - 2 * HC);
+            const uint64_t nty = (rows + (f->TH_ - 2 * f->T_) - 1) / (f->TH_ - 2 * f->T_);
+            f->chg_bytes_ = (size_t)round_up(ntx * nty, 256);
+        }
         for (int i = 0; i < 2 && ok; ++i) {
             ok = cudaMalloc(&f->chg_[i], f->chg_bytes_) == cudaSuccess && cudaMemset(f->chg_[i], 1, f->chg_bytes_) == cudaSuccess;
         }
@@ -853,25 +878,7 @@ int Field::launch_pass_3d(uint32_t it0, uint32_t count, bool check_last)
     p.BH = (uint32_t)TH_;
     p.ntx = (uint32_t)((gm_[2] + k3OutW - 1) / k3OutW);
     p.nty = (uint32_t)((gm_[1] + (p.BH - 2 * k3HR) - 1) / (p.BH - 2 * k3HR));
-    // Layers per CTA: a CTA costs (its layers + the 2 * 2 halo layers); the grid runs in waves of
-    // ctas_per_sm_ CTAs per SM.  Take the split along x0 with the cheapest estimated pass.
-    {
-        const uint64_t tiles_xy = (uint64_t)p.ntx * p.nty;
-        const uint64_t slots = (uint64_t)ctas_per_sm_ * (uint64_t)sms_;
-        uint64_t best_cost = 0;
-        uint32_t best_chunk = (uint32_t)rows_;
-        const uint64_t max_ntz = std::max<uint64_t>(1, std::min<uint64_t>(256, rows_ / 4));
-        for (uint64_t ntz = 1; ntz <= max_ntz; ++ntz) {
-            const uint64_t chunk = (rows_ + ntz - 1) / ntz;
-            const uint64_t ctas = tiles_xy * ((rows_ + chunk - 1) / chunk);
-            const uint64_t cost = ((ctas + slots - 1) / slots) * (chunk + 2 * k3HR + 2);
-            if (best_cost == 0 || cost < best_cost) {
-                best_cost = cost;
-                best_chunk = (uint32_t)chunk;
-            }
-        }
-        p.zchunk = best_chunk;
-    }
+    p.zchunk = zchunk_;
     const uint32_t ntz = (uint32_t)((rows_ + p.zchunk - 1) / p.zchunk);
     p.count = count;
     p.it0 = it0;
@@ -887,22 +894,40 @@ int Field::launch_pass_3d(uint32_t it0, uint32_t count, bool check_last)
         return kKernelExecution;
     }
     const size_t smem = sweep3d_smem_bytes(p.BH);
-    if (!attr_done_) {  // per device, so per field
-        if (!allow_smem(sweep3d_kernel<StrictMath>, smem) || !allow_smem(sweep3d_kernel<FastMath>, smem)) {
-            cudaGetLastError();
-            return kInvalidCudaParam;
-        }
-        attr_done_ = true;
-    }
     const uint32_t grid = p.ntx * p.nty * ntz;
+    p.ntz = ntz;
+    const bool track = tracking_ && skip_static_ && chg_[0] != nullptr && (size_t)grid <= chg_bytes_ && p.zchunk >= 2u * k3HR;
+    if (track) {
+        if (chg_stale_) {
+            if (cudaMemsetAsync(chg_[0], 1, chg_bytes_, stream_) != cudaSuccess ||
+                cudaMemsetAsync(chg_[1], 1, chg_bytes_, stream_) != cudaSuccess) {
+                cudaGetLastError();
+                return kKernelExecution;
+            }
+            chg_stale_ = false;
+        }
+        p.chg_prev = chg_[cur_];
+        p.chg_out = chg_[cur_ ^ 1];
+        p.skipped = &ctrl_->skipped;
+    } else {
+        chg_stale_ = true;
+    }
     if (cfg_.math == MATH_STRICT) {
         StrictMath m;
         m.init(kLog6);
-        sweep3d_kernel<StrictMath><<<grid, k3Threads, smem, stream_>>>(tmap_[cur_], p, m);
+        if (track) sweep3d_kernel<StrictMath, true><<<grid, k3Threads, smem, stream_>>>(tmap_[cur_], p, m);
+        else sweep3d_kernel<StrictMath><<<grid, k3Threads, smem, stream_>>>(tmap_[cur_], p, m);
     } else {
         FastMath m;
         m.ln2n = 1.791759469228055f;
-        sweep3d_kernel<FastMath><<<grid, k3Threads, smem, stream_>>>(tmap_[cur_], p, m);
+        if (track) sweep3d_kernel<FastMath, true><<<grid, k3Threads, smem, stream_>>>(tmap_[cur_], p, m);
+        else sweep3d_kernel<FastMath><<<grid, k3Threads, smem, stream_>>>(tmap_[cur_], p, m);
+    }
+    if (track && count < 2) {   // one colour only: see launch_pass_2d
+        if (cudaMemsetAsync(chg_[cur_ ^ 1], 1, chg_bytes_, stream_) != cudaSuccess) {
+            cudaGetLastError();
+            return kKernelExecution;
+        }
     }
     launches_++;
     if (cudaGetLastError() != cudaSuccess) {

@@ -193,6 +193,7 @@ private:
     int T_ = 4, TH_ = 96, NT_ = 256;
     int sms_ = 148;
     int ctas_per_sm_ = 2;        // 3-D: resident CTAs per SM of the sweep kernel (occupancy query)
+    uint32_t zchunk_ = 0;        // 3-D: owned layers per CTA (the split along x0, fixed at creation)
     uint64_t launches_ = 0;
     bool attr_done_ = false;
     size_t device_bytes_ = 0;

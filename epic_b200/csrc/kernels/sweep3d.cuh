@@ -62,6 +62,12 @@ struct Sweep3DParams {
     float *peer_up;            // layer 0 of the upper neighbour's ghost-below region
     float *peer_down;          // layer 0 of the lower neighbour's ghost-above region
     uint32_t halo_layers;
+    // static-block skipping (TRACK kernels): one byte per CTA, as in Sweep2DParams; the neighbourhood is the
+    // 3 x 3 x 3 block of CTAs around this one
+    const uint8_t *chg_prev;
+    uint8_t *chg_out;
+    uint32_t *skipped;
+    uint32_t ntz;              // chunks along x0
 };
 
 // [6 layer-tiles][6 nibble tiles][MathTables][6 mbarriers][8 warp maxima]
@@ -76,11 +82,12 @@ __device__ __forceinline__ void fence_proxy_async_smem()
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-template <class Math>
+template <class Math, bool TRACK>
 struct Rows3D {
     const Math &math;
     int lane;
     float dmax;
+    bool chg;          // TRACK: some update of this lane changed a value
 
     // One LDS.128 per lane (conflict-free across the warp).  Written in PTX because the compiler otherwise
     // narrows a float4 load of which only two components are used into two LDS.32 with a 16-byte lane stride
@@ -114,12 +121,18 @@ struct Rows3D {
             const float nz = math.update6(m.z, q.z, a.z, c.z, b.y, b.w);
             if (active & 1u) nw.x = nx;
             if (active & 4u) nw.z = nz;
+            if (TRACK) {
+                chg = chg || (__float_as_uint(nw.x) != __float_as_uint(b.x)) || (__float_as_uint(nw.z) != __float_as_uint(b.z));
+            }
         } else {
             const float right = __shfl_down_sync(0xffffffffu, b.x, 1);
             const float ny = math.update6(m.y, q.y, a.y, c.y, b.x, b.z);
             const float nq = math.update6(m.w, q.w, a.w, c.w, b.z, right);
             if (active & 2u) nw.y = ny;
             if (active & 8u) nw.w = nq;
+            if (TRACK) {
+                chg = chg || (__float_as_uint(nw.y) != __float_as_uint(b.y)) || (__float_as_uint(nw.w) != __float_as_uint(b.w));
+            }
         }
         if (CHECK && chk) {
             // |prev - new| is 0 for cells that were not updated
@@ -206,12 +219,40 @@ struct Rows3D {
     }
 };
 
-template <class Math>
+template <class Math, bool TRACK = false>
 __global__ void __launch_bounds__(k3Threads, 2)
-sweep3d_kernel(const __grid_constant__ CUtensorMap src_map, const Sweep3DParams p, const Math math_in)
+sweep3d_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ Sweep3DParams p,
+               const __grid_constant__ Math math_in)
 {
     if (*p.ctrl_done) {
         return;  // a previous check sweep already met the termination rule
+    }
+    if (TRACK) {
+        // Skip this CTA's column chunk when no update of the previous pass changed a value in any of the 27
+        // chunks around it (see Sweep2DParams::chg_prev); chunks that read ghost layers always run.
+        const int txy_n = (int)(p.ntx * p.nty);
+        const int cz = blockIdx.x / txy_n, cxy = blockIdx.x % txy_n;
+        const int cx = cxy % (int)p.ntx, cy = cxy / (int)p.ntx;
+        const bool reads_ghost = (cz == 0 && p.grow0 + (int64_t)p.own_lo > 0) ||
+                                 (cz == (int)p.ntz - 1 && p.grow0 + (int64_t)p.own_hi < (int64_t)p.m0);
+        uint32_t any = reads_ghost ? 1u : 0u;
+        for (int dz = -1; dz <= 1; ++dz) {
+            for (int dy = -1; dy <= 1; ++dy) {
+                for (int dx = -1; dx <= 1; ++dx) {
+                    const int x = cx + dx, y = cy + dy, z = cz + dz;
+                    if (x >= 0 && x < (int)p.ntx && y >= 0 && y < (int)p.nty && z >= 0 && z < (int)p.ntz) {
+                        any |= p.chg_prev[(z * (int)p.nty + y) * (int)p.ntx + x];
+                    }
+                }
+            }
+        }
+        if (any == 0u) {
+            if (threadIdx.x == 0) {
+                p.chg_out[blockIdx.x] = 0;
+                atomicAdd(p.skipped, 1u);
+            }
+            return;
+        }
     }
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int BH = (int)p.BH;
@@ -303,7 +344,7 @@ sweep3d_kernel(const __grid_constant__ CUtensorMap src_map, const Sweep3DParams 
 
     Math math = math_in;
     math.bind(tables);
-    Rows3D<Math> rows{math, lane, 0.0f};
+    Rows3D<Math, TRACK> rows{math, lane, 0.0f, false};
 
     const int col = lane * 4;
     const bool lane_out = col >= k3HC && col < k3W - k3HC;      // lanes 1 .. 30
@@ -412,6 +453,12 @@ sweep3d_kernel(const __grid_constant__ CUtensorMap src_map, const Sweep3DParams 
         }
     }
 
+    if (TRACK) {
+        const int any = __syncthreads_or(rows.chg ? 1 : 0);
+        if (tid == 0) {
+            p.chg_out[blockIdx.x] = any ? 1 : 0;
+        }
+    }
     if (p.check) {
         float dmax = rows.dmax;
         for (int o = 16; o > 0; o >>= 1) {

@@ -203,8 +203,8 @@ class ShardedSolver:
             raise ValueError("epsilon must be positive and stagger non-zero")
         m_max = max(self.slab.shape) if m_max is None else m_max
         self.iteration = 0
-        if len(self.slab.shape) == 2 and hasattr(self.slab, "set_tracking"):
-            self.slab.set_tracking(True)     # tiles that stopped changing (and do not read ghost rows) are skipped
+        if hasattr(self.slab, "set_tracking"):
+            self.slab.set_tracking(True)     # tiles that stopped changing (and do not read ghost layers) are skipped
         try:
             while True:
                 to_check = (-self.iteration) % stagger
@@ -212,7 +212,7 @@ class ShardedSolver:
                 if self.delta < epsilon and self.iteration >= m_max:
                     return self.iteration, self.delta
         finally:
-            if len(self.slab.shape) == 2 and hasattr(self.slab, "set_tracking"):
+            if hasattr(self.slab, "set_tracking"):
                 self.slab.set_tracking(False)
 
 

@@ -360,12 +360,12 @@ def test_maximum_size_3d_sampled_slabs_against_oracle(libepic_built):
     _check_bands((1024, 1024, 1024), [(0, 20), (510, 530), (1004, 1024)], 6, seed=78)
 
 
-def test_static_tile_skipping_is_bit_identical_and_active(libepic_built, monkeypatch):
-    """Field::solve skips tiles whose 3x3 neighbourhood saw no update change a value in the previous pass
-    (the replayed computation is a no-op into a buffer that already holds the data).  Same iteration count,
-    delta and field with the feature off, and the feature must actually engage on a grid whose wave fronts
-    take a while to fill it."""
-    shape = (1536, 2048)
+@pytest.mark.parametrize("shape", [(1536, 2048), (200, 230, 260)])
+def test_static_tile_skipping_is_bit_identical_and_active(libepic_built, monkeypatch, shape):
+    """Field::solve skips tiles (3-D: column chunks) whose neighbourhood saw no update change a value in the
+    previous pass (the replayed computation is a no-op into a buffer that already holds the data).  Same
+    iteration count, delta and field with the feature off, and the feature must actually engage on a grid whose
+    wave fronts take a while to fill it."""
     u, locked = grids.random_obstacles(shape, 0.2, 3, seed=9)
     out = {}
     for skip in ("0", "1"):

@@ -83,8 +83,6 @@ class LocalGroup:
                                         (3, "random48x3")])
 def test_slabs_on_one_gpu_bit_identical(golden, libepic_built, world, case, p2p, tracking):
     u, locked, eps, stagger = common.case_input(case)
-    if tracking and u.ndim == 3:
-        pytest.skip("static-tile skipping is a 2-D feature")
     grp = LocalGroup(u.shape, world, p2p=p2p, tracking=tracking)
     grp.upload(u, locked)
     done = 0
