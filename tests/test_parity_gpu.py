@@ -397,3 +397,25 @@ def test_every_tile_geometry_gives_the_same_bits(golden, libepic_built, monkeypa
     s.close()
     s = common.check_complete(make_gpu, "proc_maze", golden["proc_maze"])
     s.close()
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (2, 2), (3, 3), (1, 50), (50, 1), (2, 7), (3, 300), (300, 3), (4, 4),
+                                   (1, 1, 1), (3, 3, 3), (2, 5, 9), (5, 2, 9), (9, 5, 2), (4, 4, 4)])
+def test_degenerate_grids_match_the_oracle(libepic_built, shape):
+    """Grids with no interior (a dimension below 3) are legal inputs of the reference: its loops simply do not
+    run.  The device path must agree: nothing changes, delta is 0, the iteration counter still advances; with
+    the smallest interiors (3 and 4 cells across) the few free cells follow the oracle bit for bit."""
+    rng = np.random.RandomState(sum(shape) * 7 + len(shape))
+    u = (-30.0 * rng.random_sample(shape)).astype(np.float32)
+    locked = (rng.random_sample(shape) < 0.3).astype(np.uint32)
+    u[locked == 1] = np.where(rng.random_sample(int(locked.sum())) < 0.5, 0.0, -1e6).astype(np.float32)
+    h = Harmonic(u.copy(), locked.copy(), 1e-3, 3)
+    o = orc.Oracle(u.copy(), locked.copy(), 1e-3, 3)
+    h.initialize_gpu()
+    h.run_iterations(7, "gpu")
+    o.run_iterations(7)
+    h.get_potential_values_gpu()
+    h.uninitialize_gpu()
+    assert h.currentIteration == o.iteration == 7
+    assert np.array_equal(h.field, o.u)
+    assert h.delta == o.delta
