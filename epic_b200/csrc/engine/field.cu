@@ -808,7 +808,7 @@ int Field::launch_pass_2d(uint32_t it0, uint32_t count, bool check_last)
     } else {
         chg_stale_ = true;
     }
-    const int mode = (track ? kTrack : kPlain) | (kernel_sync ? kP2P : kPlain);
+    const int mode = (track ? kTrack : kPlain) | (has_peers() ? kP2P : kPlain);
 #define EPIC_LAUNCH_2D(MATH, NT, MODE) \
     sweep2d_kernel<MATH, NT, MODE><<<grid, NT, smem, stream_>>>(tmap_[cur_], p, m)
 #define EPIC_LAUNCH_2D_MODES(MATH, NT)                                   \

@@ -64,6 +64,7 @@ struct alignas(16) StrictMath {
     double c0, c1, c2; // kExpC0..2
     double ln2, a0, a1, a2;
     const MathTables *t;
+    static constexpr bool kUsesTables = true;
 
     __host__ __device__ void init(double log_2n)
     {
@@ -173,6 +174,7 @@ struct alignas(16) StrictMath {
 
 struct FastMath {
     float ln2n;  // (float) log(2n)
+    static constexpr bool kUsesTables = false;
 
     __device__ __forceinline__ void bind(const MathTables *) {}
 

@@ -272,7 +272,8 @@ struct RowCtx {
     }
 };
 
-// MODE: bit 0 = static-tile skipping (kTrack), bit 1 = in-kernel ordering of passes between GPUs (kP2P).
+// MODE: bit 0 = static-tile skipping (kTrack), bit 1 = peer stores into the neighbouring slabs (kP2P), with the
+// passes ordered between the GPUs inside the kernel when p.p2p_sync is set.
 // Compile-time, because either costs registers that the plain single-slab kernel cannot spare (the strict
 // variant runs at its 64-register cap: carrying the P2P state through the row loop cost it 6 %).
 enum { kPlain = 0, kTrack = 1, kP2P = 2 };
@@ -287,7 +288,7 @@ sweep2d_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
     if (*p.ctrl_done) {
         return;  // a previous check sweep already met the termination rule
     }
-    constexpr bool p2p = P2P;
+    const bool p2p = P2P && p.p2p_sync != 0;    // edge tile rows first only when they synchronise in the kernel
     const int tx = blockIdx.x % p.ntx, ty = tile_row_of(blockIdx.x / p.ntx, (int)p.nty, p2p);
     const int by0 = (int)p.own_lo + ty * (int)p.out_h - (int)p.T;  // buffer row of tile row 0
     if (TRACK) {
@@ -328,8 +329,8 @@ sweep2d_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int gx0 = tx * (int)p.out_w - (int)p.HC;                 // grid column of tile column 0
     // does this tile read the ghost rows of / store into a neighbour?
-    const bool edge_up = P2P && p.signal_up != nullptr && by0 < (int)p.own_lo;
-    const bool edge_dn = P2P && p.signal_dn != nullptr && by0 + (int)p.TH > (int)p.own_hi;
+    const bool edge_up = P2P && p.p2p_sync != 0 && p.signal_up != nullptr && by0 < (int)p.own_lo;
+    const bool edge_dn = P2P && p.p2p_sync != 0 && p.signal_dn != nullptr && by0 + (int)p.TH > (int)p.own_hi;
 
     if (tid == 0) {
         mbar_init(bar, 1);
@@ -363,8 +364,10 @@ sweep2d_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
         }
     }
 
-    // While the TMA is in flight: libm tables and the tile's may-update nibbles.
-    load_math_tables(tables, tid, NT);
+    // While the TMA is in flight: libm tables (strict arithmetic only) and the tile's may-update nibbles.
+    if (Math::kUsesTables) {
+        load_math_tables(tables, tid, NT);
+    }
     {
         const int w0 = gx0 >> 5;        // floor division, gx0 may be negative
         const int sh = gx0 - (w0 << 5); // 0, 4, ..., 28
@@ -440,35 +443,39 @@ sweep2d_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
     }
 
     // Write the output region (all of it, locked cells included: dst is a different buffer).
-    // A warp stores whole rows (lane = float4 group, two groups per lane): no per-item index arithmetic.
+    // A warp stores whole rows (lane = float4 group, two groups per lane): the per-lane source and
+    // destination advance by a constant per row, no per-item index arithmetic.  Only kernels built for peer
+    // stores (kP2P) carry the code that mirrors the slab's edge rows into the neighbours.
     {
         const int r_end = min((int)p.TH - (int)p.T, (int)p.own_hi - by0);
         const int c_end = min(kTileW - (int)p.HC, (int)p.pitch - gx0);
-        for (int r = max((int)p.T, (int)p.own_lo - by0) + warp; r < r_end; r += NT / 32) {
-            const int b = by0 + r;
-            const float *trow = tile + r * kTileW;
-            float *drow = p.dst + (size_t)b * p.pitch + gx0;
-            float *urow = nullptr, *lrow = nullptr;
-            if (p.peer_up != nullptr && b < (int)(p.own_lo + p.halo_rows)) {
-                urow = p.peer_up + (size_t)(b - (int)p.own_lo) * p.pitch + gx0;
-            }
-            if (p.peer_down != nullptr && b >= (int)(p.own_hi - p.halo_rows)) {
-                lrow = p.peer_down + (size_t)(b - (int)(p.own_hi - p.halo_rows)) * p.pitch + gx0;
-            }
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                const int c = (int)p.HC + lane * 4 + k * 128;
-                if (c < c_end) {
-                    const float4 v = *reinterpret_cast<const float4 *>(trow + c);
-                    *reinterpret_cast<float4 *>(drow + c) = v;
-                    if (urow != nullptr) {
-                        *reinterpret_cast<float4 *>(urow + c) = v;
-                    }
-                    if (lrow != nullptr) {
-                        *reinterpret_cast<float4 *>(lrow + c) = v;
-                    }
+        const int r0 = max((int)p.T, (int)p.own_lo - by0) + warp;
+        const int c0 = (int)p.HC + lane * 4;
+        const bool in0 = c0 < c_end, in1 = c0 + 128 < c_end;
+        const float *trow = tile + r0 * kTileW + c0;
+        float *drow = p.dst + (size_t)(by0 + r0) * p.pitch + (gx0 + c0);
+        const size_t dstep = (size_t)(NT / 32) * p.pitch;
+        for (int r = r0; r < r_end; r += NT / 32) {
+            float4 v0, v1;
+            if (in0) v0 = *reinterpret_cast<const float4 *>(trow);
+            if (in1) v1 = *reinterpret_cast<const float4 *>(trow + 128);
+            if (in0) *reinterpret_cast<float4 *>(drow) = v0;
+            if (in1) *reinterpret_cast<float4 *>(drow + 128) = v1;
+            if (P2P) {
+                const int b = by0 + r;
+                if (p.peer_up != nullptr && b < (int)(p.own_lo + p.halo_rows)) {
+                    float *urow = p.peer_up + (size_t)(b - (int)p.own_lo) * p.pitch + (gx0 + c0);
+                    if (in0) *reinterpret_cast<float4 *>(urow) = v0;
+                    if (in1) *reinterpret_cast<float4 *>(urow + 128) = v1;
+                }
+                if (p.peer_down != nullptr && b >= (int)(p.own_hi - p.halo_rows)) {
+                    float *lrow = p.peer_down + (size_t)(b - (int)(p.own_hi - p.halo_rows)) * p.pitch + (gx0 + c0);
+                    if (in0) *reinterpret_cast<float4 *>(lrow) = v0;
+                    if (in1) *reinterpret_cast<float4 *>(lrow + 128) = v1;
                 }
             }
+            trow += (NT / 32) * kTileW;
+            drow += dstep;
         }
     }
 

@@ -334,7 +334,9 @@ sweep3d_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
             issue_load(j);
         }
     }
-    load_math_tables(tables, tid, k3Threads);
+    if (Math::kUsesTables) {
+        load_math_tables(tables, tid, k3Threads);
+    }
     for (int j = 0; j < first_loads; ++j) {
         uint32_t lo, hi;
         mask_fetch(j, lo, hi);
