@@ -166,6 +166,7 @@ private:
     bool tracking_ = false;
     bool chg_stale_ = true;
     bool skip_static_ = true;    // EPIC_SKIP_STATIC=0 turns the feature off
+    bool track_runs_ = false;    // EPIC_SKIP_STATIC=all: also for plain run() passes (libepic update calls)
     uint64_t skipped_tiles_ = 0;
 
     FieldConfig cfg_;

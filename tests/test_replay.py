@@ -55,8 +55,11 @@ def test_harness_compiles_against_the_reference_headers_and_links_the_drop_in(li
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("skip_static", ["1", "all", "0"])
 @pytest.mark.parametrize("scenario", ["plan", "node"])
-def test_callers_on_the_gpu_match_the_reference(ours, gold, tmp_path, scenario):
+def test_callers_on_the_gpu_match_the_reference(ours, gold, tmp_path, scenario, skip_static, monkeypatch):
+    # static-tile skipping inside solves (default), also for the node's update ticks ("all"), and off
+    monkeypatch.setenv("EPIC_SKIP_STATIC", skip_static)
     if scenario == "plan":
         out = replay.run(ours, replay.plan_case(str(tmp_path)), "gpu")
         check(out, gold["plan"], extra=[("complete_gpu_result", "0")])
