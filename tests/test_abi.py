@@ -204,3 +204,17 @@ def test_legacy_sor_exports(libepic_built):
         assert np.allclose(res[name][2], np.linspace(1.0, 0.0, w), atol=1e-4)
     assert np.allclose(res["float"], res["double"], atol=1e-4)
     assert np.allclose(res["double"], res["long_double"], atol=1e-9)
+
+
+def test_slab_info_struct_matches_python_mirror(tmp_path):
+    """epic_b200_info (include/epic_b200.h) and its ctypes mirror must agree field by field."""
+    src = tmp_path / "info.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "epic_b200.h"\nint main(void){\n'
+                   + "".join('printf("%s %%zu\\n", offsetof(epic_b200_info, %s));\n' % (n, n) for n, _ in le.FieldInfo._fields_)
+                   + 'printf("sizeof %zu\\n", sizeof(epic_b200_info)); return 0; }\n')
+    exe = tmp_path / "info"
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(common.ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = dict(line.split() for line in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for name, _ in le.FieldInfo._fields_:
+        assert int(out[name]) == getattr(le.FieldInfo, name).offset, name
+    assert int(out["sizeof"]) == ct.sizeof(le.FieldInfo)
