@@ -1387,12 +1387,33 @@ int Field::paths_2d(uint32_t count, const float *starts, float step, float cd, u
             break;
         }
         running = false;
+        // One copy per launch when many streamlines are traced (their segments are scattered on the host);
+        // a single streamline copies just what it emitted.
+        const bool bulk = count > 1;
+        uint32_t most = 0;
+        if (bulk) {
+            for (uint32_t i = 0; i < count; ++i) {
+                most = std::max(most, emitted[i]);
+            }
+            if (most > 0) {
+                // the first `most` points of every streamline's segment, packed: one strided copy
+                chunk_host.resize((size_t)count * most * 2);
+                if (cudaMemcpy2D(chunk_host.data(), (size_t)most * 2 * sizeof(float), d_out, (size_t)chunk * 2 * sizeof(float),
+                                 (size_t)most * 2 * sizeof(float), count, cudaMemcpyDeviceToHost) != cudaSuccess) {
+                    cudaGetLastError();
+                    result = kMemcpyToHost;
+                    break;
+                }
+            }
+        }
         for (uint32_t i = 0; i < count; ++i) {
             if (emitted[i] > 0) {
                 const size_t old = acc[i].size();
                 acc[i].resize(old + (size_t)emitted[i] * 2);
-                if (cudaMemcpy(acc[i].data() + old, d_out + (size_t)i * chunk * 2, (size_t)emitted[i] * 2 * sizeof(float),
-                               cudaMemcpyDeviceToHost) != cudaSuccess) {
+                if (bulk) {
+                    memcpy(acc[i].data() + old, chunk_host.data() + (size_t)i * most * 2, (size_t)emitted[i] * 2 * sizeof(float));
+                } else if (cudaMemcpy(acc[i].data() + old, d_out + (size_t)i * chunk * 2,
+                                      (size_t)emitted[i] * 2 * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) {
                     cudaGetLastError();
                     result = kMemcpyToHost;
                 }
