@@ -274,8 +274,8 @@ struct RowCtx {
 
 // MODE: bit 0 = static-tile skipping (kTrack), bit 1 = peer stores into the neighbouring slabs (kP2P), with the
 // passes ordered between the GPUs inside the kernel when p.p2p_sync is set.
-// Compile-time, because either costs registers that the plain single-slab kernel cannot spare (the strict
-// variant runs at its 64-register cap: carrying the P2P state through the row loop cost it 6 %).
+// Compile-time, so that the plain single-slab kernel carries none of their code (the strict variant runs at
+// its 64-register cap, and the write-back loop without peer stores is a third of the size).
 enum { kPlain = 0, kTrack = 1, kP2P = 2 };
 
 template <class Math, int NT, int MODE = kPlain>
