@@ -13,6 +13,7 @@
 // separate IEEE operation, as in the reference's own build (libepic/Makefile:2).
 #include <math.h>
 #include <stdint.h>
+#include <cmath>
 #include <stdio.h>
 
 #include <algorithm>
@@ -304,6 +305,51 @@ int harmonic_utilities_set_cells_2d_cpu(Harmonic *harmonic, unsigned int k, unsi
         harmonic->u[c] = kValue[types[i]];
         harmonic->locked[c] = kLocked[types[i]];
     }
+    return EPIC_SUCCESS;
+}
+
+// ---- extensions: the pose list the callers build from a raw path (src/epic_nav_core_plugin.cpp:310-328,
+// src/epic_navigation_node_harmonic.cpp:655-668): world x, world y and yaw of the incoming segment per point.
+// Same float operations as the callers' loops (separate multiply and add, atan2 of the float differences
+// narrowed to float), so a client receives identical numbers.
+
+int harmonic_path_to_poses_2d(const float *path, unsigned int k, float originX, float originY, float resolution,
+                              float *poses)
+{
+    if (path == nullptr || poses == nullptr || k == 0) {
+        return EPIC_ERROR_INVALID_DATA;
+    }
+    for (unsigned int i = 0; i < k; i++) {
+        const float x = path[2 * i + 0], y = path[2 * i + 1];
+        // point 0 has no incoming segment: it takes the heading of the first one (the callers put the
+        // request's own start pose there)
+        const unsigned int a = (i == 0) ? 0 : i - 1, b = (i == 0) ? ((k > 1) ? 1 : 0) : i;
+        const float theta = std::atan2(path[2 * b + 1] - path[2 * a + 1], path[2 * b + 0] - path[2 * a + 0]);
+        poses[3 * i + 0] = originX + x * resolution;
+        poses[3 * i + 1] = originY + y * resolution;
+        poses[3 * i + 2] = theta;
+    }
+    return EPIC_SUCCESS;
+}
+
+int harmonic_compute_path_poses_2d_cpu(Harmonic *harmonic, float x, float y, float stepSize, float cdPrecision,
+                                       unsigned int maxLength, float originX, float originY, float resolution,
+                                       unsigned int &k, float *&poses)
+{
+    if (poses != nullptr) {
+        complain("harmonic_compute_path_poses_2d_cpu", "Invalid data.");
+        return EPIC_ERROR_INVALID_DATA;
+    }
+    float *raw = nullptr;
+    unsigned int kk = 0;
+    const int r = harmonic_compute_path_2d_cpu(harmonic, x, y, stepSize, cdPrecision, maxLength, kk, raw);
+    if (r != EPIC_SUCCESS) {
+        return r;
+    }
+    poses = new float[3 * (size_t)kk];
+    harmonic_path_to_poses_2d(raw, kk, originX, originY, resolution, poses);
+    delete[] raw;
+    k = kk;
     return EPIC_SUCCESS;
 }
 

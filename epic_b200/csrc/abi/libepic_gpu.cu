@@ -692,4 +692,27 @@ int harmonic_compute_path_2d_gpu(Harmonic *harmonic, float x, float y, float ste
     return ret;
 }
 
+int harmonic_compute_path_poses_2d_gpu(Harmonic *harmonic, float x, float y, float stepSize, float cdPrecision,
+                                       unsigned int maxLength, float originX, float originY, float resolution,
+                                       unsigned int &k, float *&poses)
+{
+    if (poses != nullptr) {
+        complain("harmonic_compute_path_poses_2d_gpu", "Invalid data.");
+        return EPIC_ERROR_INVALID_DATA;
+    }
+    float *raw = nullptr;
+    unsigned int kk = 0;
+    const int r = harmonic_compute_path_2d_gpu(harmonic, x, y, stepSize, cdPrecision, maxLength, kk, raw);
+    if (r != EPIC_SUCCESS) {
+        return r;
+    }
+    // the streamline is traced on the device-resident field; the pose arithmetic stays on the host so that
+    // the yaw is the host libm's atan2, as in the callers
+    poses = new float[3 * (size_t)kk];
+    harmonic_path_to_poses_2d(raw, kk, originX, originY, resolution, poses);
+    delete[] raw;
+    k = kk;
+    return EPIC_SUCCESS;
+}
+
 }  // namespace epic

@@ -160,6 +160,18 @@ class Harmonic(le.EpicHarmonic):
         le.load().harmonic_free_path_cpu(ct.byref(raw))
         return r, path
 
+    def compute_path_poses(self, x, y, stepSize, cdPrecision, maxLength, originX, originY, resolution, process='cpu'):
+        """(return code, float32 array (k, 3)): world x, world y, yaw per path point -- what the ROS callers publish."""
+        k = ct.c_uint(0)
+        raw = ct.POINTER(ct.c_float)()
+        r = getattr(le.load(), "harmonic_compute_path_poses_2d_" + process)(
+            ct.byref(self), x, y, stepSize, cdPrecision, int(maxLength), originX, originY, resolution, ct.byref(k), ct.byref(raw))
+        if r != le.EPIC_SUCCESS:
+            return r, np.zeros((0, 3), np.float32)
+        out = np.ctypeslib.as_array(raw, shape=(3 * k.value,)).copy().reshape(-1, 3)
+        le.load().harmonic_free_path_cpu(ct.byref(raw))
+        return r, out
+
     def compute_paths_gpu(self, starts, stepSize=0.2, cdPrecision=0.4, maxLength=1000000):
         """Many streamlines in one call on the device-resident field: list of (code, path array)."""
         starts = np.ascontiguousarray(starts, dtype=np.float32).reshape(-1, 2)

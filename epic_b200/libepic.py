@@ -113,6 +113,11 @@ EXTENSION_EXPORTS = {
                                      _P(ct.c_uint), _P(_P(ct.c_float))),
     "harmonic_compute_paths_2d_gpu": (_H, ct.c_uint, _P(ct.c_float), ct.c_float, ct.c_float, ct.c_uint,
                                       _P(ct.c_int), _P(ct.c_uint), _P(_P(ct.c_float))),
+    "harmonic_path_to_poses_2d": (_P(ct.c_float), ct.c_uint, ct.c_float, ct.c_float, ct.c_float, _P(ct.c_float)),
+    "harmonic_compute_path_poses_2d_cpu": (_H, ct.c_float, ct.c_float, ct.c_float, ct.c_float, ct.c_uint, ct.c_float,
+                                           ct.c_float, ct.c_float, _P(ct.c_uint), _P(_P(ct.c_float))),
+    "harmonic_compute_path_poses_2d_gpu": (_H, ct.c_float, ct.c_float, ct.c_float, ct.c_float, ct.c_uint, ct.c_float,
+                                           ct.c_float, ct.c_float, _P(ct.c_uint), _P(_P(ct.c_float))),
     "harmonic_utilities_set_occupancy_grid_2d_cpu": (_H, _P(ct.c_byte), ct.c_int, ct.c_int),
     "harmonic_utilities_set_occupancy_grid_2d_gpu": (_H, _P(ct.c_byte), ct.c_int, ct.c_int),
     "harmonic_utilities_reset_free_cells_2d_cpu": (_H,),

@@ -148,6 +148,21 @@ EPIC_API int harmonic_compute_paths_2d_gpu(Harmonic *harmonic, unsigned int numP
                                            float stepSize, float cdPrecision, unsigned int maxLength, int *results,
                                            unsigned int *k, float **paths);
 
+/* The pose list the callers build from a raw path (src/epic_nav_core_plugin.cpp:310-328,
+ * src/epic_navigation_node_harmonic.cpp:655-668): poses = [world x, world y, yaw] * k with world = origin + cell *
+ * resolution and yaw = atan2 of the incoming segment (point 0: of the first segment), in the callers' float
+ * arithmetic.  harmonic_compute_path_poses_2d_* trace the path (host field / device-resident field) and return
+ * new float[3*k], to be released with delete[] or harmonic_free_path_cpu. */
+EPIC_API int harmonic_path_to_poses_2d(const float *path, unsigned int k, float originX, float originY,
+                                       float resolution, float *poses);
+EPIC_API int harmonic_compute_path_poses_2d_cpu(Harmonic *harmonic, float x, float y, float stepSize,
+                                                float cdPrecision, unsigned int maxLength, float originX,
+                                                float originY, float resolution, EPIC_REF(unsigned int) k,
+                                                EPIC_REF(float *) poses);
+EPIC_API int harmonic_compute_path_poses_2d_gpu(Harmonic *harmonic, float x, float y, float stepSize,
+                                                float cdPrecision, unsigned int maxLength, float originX,
+                                                float originY, float resolution, EPIC_REF(unsigned int) k,
+                                                EPIC_REF(float *) poses);
 
 /* ---- Extensions: dense map ingest.  The reference's node turns every /map message into a set_cells call
  * over EVERY interior cell and implements "reset free cells" the same way (k = N scatter lists, 12 bytes per

@@ -9,6 +9,7 @@ identical for the library's CPU exports and, on a B200, for its *_gpu entry poin
 import json
 import os
 
+import numpy as np
 import pytest
 
 import common
@@ -66,3 +67,50 @@ def test_callers_on_the_gpu_match_the_reference(ours, gold, tmp_path, scenario, 
     else:
         out = replay.run(ours, replay.node_case(str(tmp_path)), "gpu")
         check(out, gold["node"], extra=[("gpu_initialised", "1"), ("gpu_uninitialised", "1")])
+
+
+def _fnv(data, h=1469598103934665603):
+    for b in data:
+        h = ((h ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
+def _plan_state(tmp_path):
+    """The Harmonic object of the plan scenario after initialize() + setGoal(), built as the harness builds it."""
+    from epic_b200.harmonic import Harmonic
+    case = replay.plan_case(str(tmp_path))
+    raw = np.fromfile(case[1], dtype=np.uint8)
+    h, w = (int(v) for v in raw[:8].view(np.uint32))
+    cost = raw[8:].reshape(h, w)
+    locked = (cost >= 250).astype(np.uint32)
+    locked[0, :] = locked[-1, :] = locked[:, 0] = locked[:, -1] = 1
+    u = np.full((h, w), -1e6, np.float32)
+    gx, gy = int(case[3]), int(case[4])
+    u[gy, gx], locked[gy, gx] = 0.0, 1
+    x = np.float32((np.float32(float(case[5])) - np.float32(replay.OX)) / np.float32(replay.RES))
+    y = np.float32((np.float32(float(case[6])) - np.float32(replay.OY)) / np.float32(replay.RES))
+    return Harmonic(u, locked, 1e-3, 100), float(x), float(y), int(np.float32(h * w) / np.float32(0.05))
+
+
+def _check_poses(hm, x, y, max_length, gold, process):
+    r, poses = hm.compute_path_poses(x, y, 0.05, 0.5, max_length, replay.OX, replay.OY, replay.RES, process)
+    assert r == 0 and len(poses) == int(gold["plan0_path_points"])
+    assert "%016x" % _fnv(poses[1:].tobytes()) == gold["plan0_path_poses"], "pose list differs from the caller's own loop"
+
+
+def test_pose_lists_equal_what_the_reference_plugin_publishes(libepic_built, gold, tmp_path):
+    """harmonic_compute_path_poses_2d_cpu against the pose hash of the replayed plugin (golden from the
+    reference sources): world coordinates and yaw in the callers' float arithmetic."""
+    hm, x, y, max_length = _plan_state(tmp_path)
+    hm.solve(process="cpu")
+    assert hm.currentIteration == int(gold["plan"]["plan0_iterations"])
+    _check_poses(hm, x, y, max_length, gold["plan"], "cpu")
+
+
+@pytest.mark.gpu
+def test_pose_lists_from_the_device_resident_field(libepic_built, gold, tmp_path):
+    hm, x, y, max_length = _plan_state(tmp_path)
+    hm.solve(process="gpu")
+    hm.initialize_gpu()
+    _check_poses(hm, x, y, max_length, gold["plan"], "gpu")
+    hm.uninitialize_gpu()
