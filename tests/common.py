@@ -1,5 +1,5 @@
 """Shared pieces of the parity tests: the inputs of the golden cases (tests/golden/golden.json was
-produced by tools/make_golden.py from the UNTOUCHED reference CPU code) and one checking routine that
+produced by tests/golden/make_golden.py from the UNTOUCHED reference CPU code) and one checking routine that
 every implementation under test goes through -- the oracle, the library's CPU exports, and the CUDA
 path through the libepic C ABI.
 

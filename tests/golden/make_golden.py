@@ -12,7 +12,7 @@ harmonic_compute_path_2d_cpu, harmonic_utilities_set_cells_2d_cpu).  Outputs:
   tests/golden/golden.json  per case: iterations, delta (exact hex), sha1 of the field bytes,
                             probe values, path lengths / hashes / sampled points
 
-Usage: python tools/make_golden.py [case ...]     (no argument = all cases; slow ones ~6 min)
+Usage: python tests/golden/make_golden.py [case ...]     (no argument = all cases; slow ones ~6 min)
 """
 import hashlib
 import json
@@ -22,7 +22,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 from epic_b200 import grids  # noqa: E402

@@ -1,6 +1,6 @@
 """Build and run tests/native/replay_callers.cpp (the ROS-free replay of the nav_core plugin and of the
 anytime node) and the inputs of its two scenarios.  Shared by tests/test_replay.py and
-tools/make_replay_golden.py."""
+tests/golden/make_replay_golden.py."""
 import os
 import subprocess
 

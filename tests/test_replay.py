@@ -3,7 +3,7 @@ the anytime node's tick + services -- replayed without ROS by tests/native/repla
 program written against the library's public headers and linked with the drop-in libepic.so.
 
 tests/golden/replay_callers.json is the output of the SAME source compiled against the reference's own
-headers and linked with the untouched reference CPU sources (tools/make_replay_golden.py); every line a
+headers and linked with the untouched reference CPU sources (tests/golden/make_replay_golden.py); every line a
 client would observe (iteration counts, delta bits, hashes of u / locked / raw paths / pose lists) must be
 identical for the library's CPU exports and, on a B200, for its *_gpu entry points."""
 import json
