@@ -16,6 +16,9 @@
 // output of a GPU run can be compared with a CPU run of the same binary and with the same binary linked
 // against the reference's CPU sources (-DREPLAY_CPU_ONLY, oracle/_ref).
 //
+// -DREPLAY_DENSE_INGEST (this library's headers only) replaces the node's two k = N set-cells lists by the dense
+// map-ingest extensions; the output must not change.
+//
 // usage: replay_callers plan map.bin cpu|gpu goal_x goal_y start_wx start_wy
 //        replay_callers node map.bin cpu|gpu goal_wx goal_wy start_wx start_wy ticks steps
 //   map.bin = uint32 height, uint32 width, height*width bytes (plan: costmap costs 0..255;
@@ -288,7 +291,18 @@ int node(const char *map, bool want_gpu, float gwx, float gwy, float swx, float 
             types.push_back(occ >= 50 ? EPIC_CELL_TYPE_OBSTACLE : EPIC_CELL_TYPE_FREE);
         }
     }
+#ifdef REPLAY_DENSE_INGEST
+    // the optional upgrade of INTEGRATION.md section 3: hand the message itself to the library
+    {
+        bool ok = harmonic_utilities_set_occupancy_grid_2d_cpu(&hm, (const signed char *)grid.data(), 50, -2) == EPIC_SUCCESS;
+        if (ok && nd.gpu) {
+            ok = harmonic_utilities_set_occupancy_grid_2d_gpu(&hm, (const signed char *)grid.data(), 50, -2) == EPIC_SUCCESS;
+        }
+        printf("map_cells %zu\nmap_set %d\n", types.size(), ok ? 1 : 0);
+    }
+#else
     printf("map_cells %zu\nmap_set %d\n", types.size(), nd.set_cells(v, types) ? 1 : 0);
+#endif
     // add one goal (world coordinates), unless it falls into an obstacle
     float gx = 0.0f, gy = 0.0f;
     world_to_map(gwx, gwy, w, h, gx, gy);
@@ -341,7 +355,17 @@ int node(const char *map, bool want_gpu, float gwx, float gwy, float swx, float 
             }
         }
     }
+#ifdef REPLAY_DENSE_INGEST
+    {
+        bool ok = harmonic_utilities_reset_free_cells_2d_cpu(&hm) == EPIC_SUCCESS;
+        if (ok && nd.gpu) {
+            ok = harmonic_utilities_reset_free_cells_2d_gpu(&hm) == EPIC_SUCCESS;
+        }
+        printf("reset_cells %zu\nreset_set %d\n", types.size(), ok ? 1 : 0);
+    }
+#else
     printf("reset_cells %zu\nreset_set %d\n", types.size(), nd.set_cells(v, types) ? 1 : 0);
+#endif
     for (unsigned t = 0; t < ticks; ++t) nd.tick(steps);
     printf("fetch3 %d\n", nd.fetch() ? 1 : 0);
     sayu("iterations3", hm.currentIteration);

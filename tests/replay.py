@@ -20,12 +20,14 @@ GOLDEN = os.path.join(common.ROOT, "tests", "golden", "replay_callers.json")
 OX, OY, RES = -12.5, 3.25, 0.05
 
 
-def build(out, include=OURS_INC, libdir=OURS_LIBDIR, lib="epic", cpu_only=False):
+def build(out, include=OURS_INC, libdir=OURS_LIBDIR, lib="epic", cpu_only=False, dense_ingest=False):
     """g++ with the reference Makefile's arithmetic (no FMA contraction, no fast-math)."""
     cmd = ["g++", "-std=c++11", "-O2", "-ffp-contract=off", "-I", include, SRC, "-o", out,
            "-L", libdir, "-l" + lib, "-Wl,-rpath," + libdir, "-lm"]
     if cpu_only:
         cmd.insert(1, "-DREPLAY_CPU_ONLY")
+    if dense_ingest:
+        cmd.insert(1, "-DREPLAY_DENSE_INGEST")
     subprocess.run(cmd, check=True)
     return out
 

@@ -27,6 +27,12 @@ def ours(libepic_built, tmp_path_factory):
     return replay.build(str(tmp_path_factory.mktemp("replay") / "replay_ours"))
 
 
+@pytest.fixture(scope="module")
+def ours_dense(libepic_built, tmp_path_factory):
+    """The same harness with the node's scatter lists replaced by the dense map-ingest extensions."""
+    return replay.build(str(tmp_path_factory.mktemp("replay") / "replay_dense"), dense_ingest=True)
+
+
 def check(out, gold, extra=()):
     for k, v in gold.items():
         assert out.get(k) == v, "%s: got %s, the reference gives %s" % (k, out.get(k), v)
@@ -38,6 +44,16 @@ def check(out, gold, extra=()):
 def test_callers_on_the_cpu_exports_match_the_reference(ours, gold, tmp_path, scenario):
     case = replay.plan_case(str(tmp_path)) if scenario == "plan" else replay.node_case(str(tmp_path))
     check(replay.run(ours, case, "cpu"), gold[scenario])
+
+
+def test_node_with_dense_map_ingest_is_indistinguishable_on_the_cpu_exports(ours_dense, gold, tmp_path):
+    check(replay.run(ours_dense, replay.node_case(str(tmp_path)), "cpu"), gold["node"])
+
+
+@pytest.mark.gpu
+def test_node_with_dense_map_ingest_is_indistinguishable_on_the_gpu(ours_dense, gold, tmp_path):
+    out = replay.run(ours_dense, replay.node_case(str(tmp_path)), "gpu")
+    check(out, gold["node"], extra=[("gpu_initialised", "1"), ("gpu_uninitialised", "1")])
 
 
 @pytest.mark.skipif(not os.path.isdir(replay.REF_INC), reason="the reference tree is only present in the build container")
