@@ -17,8 +17,20 @@ one half-sweep; algorithmic traffic 8 B per update.
             N > 1: the slab API, each rank moving its own slab]
   roofline  HBM roofline of the sweep kernel: 8 B x updates / kernel time vs MEASURED_PEAKS.json
   cpu_baseline  the reference's own CPU code (oracle/_ref, built from the untouched sources) on this host
+  gpu_baseline  the reference's own GPU code (harmonic_gpu.cu recompiled for sm_100a, oracle/_ref) on this B200:
+                harmonic_update_gpu x K on the same grid and harmonic_complete_gpu on maps/maze.png, beside this
+                library's figures for the same calls (N = 1 only; a subprocess under a timeout)
+  tte_* / field_sha1*  time to epsilon (every tile swept / static tiles skipped), its iteration count, and the sha1
+                of the converged field gathered from all ranks -- compared with the hash committed for N = 1
+                (tests/golden/bench_fields.json), so that a scaling run carries its own correctness evidence
+  abi_multi     (N > 1, rank 0 after the ranks have finished) the same grid through the libepic C ABI alone, with
+                EPIC_DEVICES naming all N GPUs: the single-process sharding inside the library (engine/grid.cu)
 The grid (1 GiB of potentials per buffer) is 8x larger than L2, so nothing survives between passes.
+
+  --workload maze --size 65536 --gpus 8   BASELINE.json config 4 (procedural maze, 16 GiB field)
+  --dims 3 --size 1024 [--gpus N]         BASELINE.json config 5
 """
+import hashlib
 import argparse
 import json
 import os
@@ -137,11 +149,30 @@ def grid_shape(args):
     return (args.size,) * args.dims
 
 
-def workload(args):
+def make_grid(args, row0=0, rows=None):
+    """(u, locked) of rows [row0, row0 + rows) of the bench grid."""
+    from epic_b200 import grids
+    shape = grid_shape(args)
+    if args.workload == "maze":
+        return grids.procedural_maze(shape, corridor=args.corridor, wall=2, goals=args.goals, seed=1234, row0=row0, rows=rows)
+    return grids.random_obstacles(shape, 0.2, args.goals, seed=1234, row0=row0, rows=rows)
+
+
+def workload_name(args):
+    shape = "x".join(str(s) for s in grid_shape(args))
+    if args.workload == "maze":
+        return "synthetic %s procedural maze (corridor %d, wall 2, %d goals, seed 1234)" % (shape, args.corridor, args.goals)
+    return "synthetic %s random-obstacle grid (p=0.2, %d goals, seed 1234)" % (shape, args.goals)
+
+
+def workload(args, sweeps_per_step=None):
     shape = grid_shape(args)
     cells = int(np.prod(shape, dtype=np.int64))
-    return {"workload": "synthetic %s random-obstacle grid (p=0.2, 64 goals, seed 1234), %s-slab sharded"
-                        % ("x".join(str(s) for s in shape), "row" if args.dims == 2 else "x0"),
+    if sweeps_per_step is not None:     # the reference arm: its step is one half-sweep of a band
+        return {"workload": workload_name(args) + ", %s-slab sharded" % ("row" if args.dims == 2 else "x0"),
+                "grid": list(shape), "epsilon": 1e-3, "stagger": SWEEPS_PER_STEP, "sweeps_per_step": sweeps_per_step,
+                "parallelism": "host cores"}
+    return {"workload": workload_name(args) + ", %s-slab sharded" % ("row" if args.dims == 2 else "x0"),
             "grid": list(shape), "epsilon": 1e-3, "stagger": SWEEPS_PER_STEP,
             "sweeps_per_step": SWEEPS_PER_STEP, "updates_per_step": cells // 2 * SWEEPS_PER_STEP,
             "parallelism": "%s-slab x%d" % ("row" if args.dims == 2 else "x0", args.gpus),
@@ -152,11 +183,11 @@ def workload(args):
 # ---------------------------------------------------------------------------------------------------
 # reference arm: the reference's own CPU code on the host cores
 
-def cpu_reference_rate(size, rows, sweeps, warmup=0, dims=2):
+def cpu_reference_rate(args, rows, sweeps, warmup=0):
     """(updates/s, description) of the reference CPU half-sweep over the first `rows` x0-layers of the grid."""
-    from epic_b200 import grids
     from oracle import oracle as orc
-    u, locked = grids.random_obstacles((size,) * dims, 0.2, 64, seed=1234, row0=0, rows=rows)
+    size, dims = args.size, args.dims
+    u, locked = make_grid(args, 0, rows)
     locked[-1] = 1
     if orc.have_ref():
         solver, kind, cores = orc.Reference(u, locked, 1e-3, SWEEPS_PER_STEP), "reference", 1
@@ -183,18 +214,98 @@ def run_reference(args):
     # one step = one half-sweep over a band sized so that the whole run stays within ~150 s at ~25 M updates/s
     budget_updates = 150.0 * 25e6 / max(1, args.steps + args.warmup)
     rows = int(min(args.size, max(8, budget_updates / (float(args.size) ** (args.dims - 1) / 2.0))))
-    rate, dt, kind, cores, what = cpu_reference_rate(args.size, rows, args.steps, args.warmup, args.dims)
+    rate, dt, kind, cores, what = cpu_reference_rate(args, rows, args.steps, args.warmup)
     value = rate / 1e9
     sample = "%d half-sweeps (steps) over x0 = 0..%d of the %s grid; %s" % (
         args.steps, rows - 1, "x".join(str(v) for v in grid_shape(args)), what)
     line = {"impl": "reference", "metric": "Gcell-updates/s", "value": value, "unit": "Gcell-updates/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload(args), "gpu_launches": 0,
+            "config": dict(workload(args, sweeps_per_step=1), step="one half-sweep (harmonic_update_cpu) over x0 = 0..%d; "
+                           "the rate is per lattice-site update, the unit the native arm reports" % (rows - 1),
+                           updates_per_step=int((rows - 2) * float(args.size - 2) ** (args.dims - 1) / 2.0)),
+            "gpu_launches": 0,
             "cpu_baseline": {"value": value, "unit": "Gcell-updates/s", "cores": cores, "kind": kind, "sample": sample,
                              "host_cores": os.cpu_count()},
             "e2e": {"value": value, "unit": "Gcell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+HASH_BAND = 1024      # x0-layers per band of the field hash: slab boundaries of 1/2/4/8 ranks fall on band boundaries
+
+
+def band_digests(own, row0):
+    """sha1 digests of the 1024-layer bands of this rank's owned layers (row0 must be a band boundary unless the
+    rank owns everything)."""
+    out = []
+    for a in range(0, own.shape[0], HASH_BAND):
+        out.append(((row0 + a) // HASH_BAND, hashlib.sha1(np.ascontiguousarray(own[a:a + HASH_BAND]).tobytes()).hexdigest()))
+    return out
+
+
+def field_hash(digests):
+    """One hash of the whole field from the per-band digests of all ranks (independent of the partition)."""
+    h = hashlib.sha1()
+    for _, d in sorted(digests):
+        h.update(bytes.fromhex(d))
+    return h.hexdigest()
+
+
+def committed_fields():
+    path = os.path.join(ROOT, "tests", "golden", "bench_fields.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f)
+    return {}
+
+
+def source_stamp():
+    """Hash of the sweep-kernel sources: profiles/ncu_traffic.json carries the stamp of the kernels it was measured
+    on, and a stale measurement is reported as null instead of silently describing another kernel."""
+    h = hashlib.sha1()
+    for name in ("sweep2d.cuh", "sweep3d.cuh", "math_policies.cuh", "strict_math.h"):
+        with open(os.path.join(ROOT, "epic_b200", "csrc", "kernels", name), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
+def reference_gpu_baseline(args):
+    """The reference's own GPU path (recompiled for sm_100a) on this box, in a subprocess under a timeout, and this
+    library's time for the same harmonic_complete_gpu call on maps/maze.png."""
+    from oracle import ref_gpu
+    if not ref_gpu.available():
+        return {"unavailable": "oracle/_ref/libepic_ref_gpu.so was not built (no /root/reference at build time)"}
+    out = {}
+
+    def sub(argv, timeout):
+        try:
+            r = subprocess.run([sys.executable, "-m", "oracle.ref_gpu"] + argv, cwd=ROOT, capture_output=True, text=True,
+                               timeout=timeout)
+            lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            return json.loads(lines[-1]) if lines else {"error": (r.stderr or "no output")[-300:]}
+        except subprocess.TimeoutExpired:
+            return {"error": "timed out after %d s" % timeout}
+    if args.dims == 2 and args.size <= 16384:
+        out["sweeps"] = sub(["sweeps", "--size", str(args.size), "--steps", "10", "--warmup", "2"], 300)
+    out["maze"] = sub(["complete", "--map", "maze"], 180)
+    # ours, same call, same map
+    try:
+        from epic_b200 import grids
+        from epic_b200.harmonic import Harmonic
+        maps = np.load(os.path.join(ROOT, "tests", "golden", "maps.npz"))
+        u, locked = grids.grid_from_image(maps["maze"])
+        best = None
+        for _ in range(3):
+            h = Harmonic(u.copy(), locked.copy(), 1e-3, 100)
+            t0 = time.perf_counter()
+            h.solve(process="gpu")
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        out["maze_ours"] = {"seconds": best, "iterations": int(h.currentIteration), "delta": float(h.delta),
+                            "what": "harmonic_complete_gpu of this library on the same map (strict unless EPIC_MATH says otherwise), best of 3"}
+    except Exception as e:      # noqa: BLE001
+        out["maze_ours"] = {"error": str(e)[:200]}
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -230,7 +341,7 @@ def run_native(args):
     row0, nrows = _partition(size, world, rank)
     ghost = (4 if args.dims == 2 else 2) if world > 1 else 0
     lo, hi = max(0, row0 - ghost), min(size, row0 + nrows + ghost)
-    u_held, locked_held = grids.random_obstacles(shape, 0.2, 64, seed=1234, row0=lo, rows=hi - lo)
+    u_held, locked_held = make_grid(args, lo, hi - lo)
     u_pin = torch.from_numpy(u_held).pin_memory()
     l_pin = torch.from_numpy(locked_held.view(np.int32)).pin_memory()
     u_host, l_host = u_pin.numpy(), l_pin.numpy().view(np.uint32)
@@ -291,12 +402,18 @@ def run_native(args):
         kern_ms = start.elapsed_time(stop) / passes
         own_updates_per_pass = slab.rows * layer_cells // 2 * info["sweeps_per_pass"]
         achieved = own_updates_per_pass * ALGO_BYTES_PER_UPDATE / (kern_ms * 1e-3) / 1e9
-        traffic = None
+        traffic, traffic_note = None, "no ncu measurement for this configuration"
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-        if os.path.exists(tpath) and size == 16384 and args.dims == 2:
+        if os.path.exists(tpath) and size == 16384 and args.dims == 2 and args.workload == "random":
             with open(tpath) as f:
-                traffic = json.load(f).get(math)
+                tj = json.load(f)
+            if tj.get("source_stamp") == source_stamp():
+                traffic = tj.get(math)
                 traffic = traffic / world if traffic else None
+                traffic_note = tj.get("note")
+            else:
+                traffic_note = "profiles/ncu_traffic.json was measured on other kernel sources (stamp %s, now %s): not reported" % (
+                    tj.get("source_stamp"), source_stamp())
         # the throw-away passes above ran without halo exchange: restore a consistent state
         slab.upload(u_host, l_host)
         solver.iteration = 0
@@ -367,10 +484,26 @@ def run_native(args):
                 seconds = max_over_ranks((time.perf_counter() - t0) * 1e3) / 1e3
                 return seconds, it, delta, converged, slab.field.info()["skipped_tiles"] - skipped0
 
-            sec_all, it_all, delta_all, conv_all, _ = run_to_epsilon(False)
+            if args.tte_all_tiles:
+                sec_all, it_all, delta_all, conv_all, _ = run_to_epsilon(False)
+            else:
+                sec_all, it_all, delta_all, conv_all = None, None, None, None
             tte = {"seconds": sec_all, "iterations": it_all, "delta": delta_all, "epsilon": 1e-3, "converged": conv_all,
                    "note": "termination rule of harmonic_execute_gpu; excludes H2D/D2H; every tile swept in every pass"}
             sec, it, delta, conv, skipped = run_to_epsilon(True)
+            # correctness evidence that travels with the number: the converged field, hashed band by band on the
+            # rank that owns it, compared with the hash committed for this workload at N = 1
+            digests = band_digests(slab.download_owned(), slab.row0)
+            skipped_all = [int(skipped)]
+            if world > 1:
+                gathered = [None] * world
+                dist.all_gather_object(gathered, (digests, int(skipped)))
+                digests = [d for part, _ in gathered for d in part]
+                skipped_all = [sk for _, sk in gathered]
+            tte["field_sha1"] = field_hash(digests)
+            tte["tiles_skipped_by_rank"] = skipped_all
+            if it_all is None:
+                it_all, delta_all = it, delta
             tte["with_static_tile_skipping"] = {
                 "seconds": sec, "iterations": it, "delta": delta,
                 "identical_to_all_tiles_run": bool(it == it_all and delta == delta_all),
@@ -398,33 +531,128 @@ def run_native(args):
     main_res = measure(args.math, args.tte)
     other = None
     if not args.single_mode:
-        other = measure("fast" if args.math == "strict" else "strict", False)
+        other = measure("fast" if args.math == "strict" else "strict", args.tte and args.tte_both_modes)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu_rows = size if args.dims == 2 else min(size, 256)
-        rate, dt, kind, cores, what = cpu_reference_rate(size, cpu_rows, 4, dims=args.dims)
+        rate, dt, kind, cores, what = cpu_reference_rate(args, cpu_rows, 4)
         cpu = {"value": rate / 1e9, "unit": "Gcell-updates/s", "cores": cores, "kind": kind, "host_cores": os.cpu_count(),
                "sample": "4 half-sweeps of x0 = 0..%d of the %s grid (%.1f s); %s" % (
                    cpu_rows - 1, "x".join(str(v) for v in shape), dt, what)}
 
-    if rank == 0:
-        line = {"metric": "Gcell-updates/s", "value": main_res["value"], "unit": "Gcell-updates/s", "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": main_res["ms_per_step"],
-                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": dict(workload(args), **main_res["config_extra"]),
-                "clocks": main_res["clocks"], "e2e": main_res["e2e"], "gpu_launches": main_res["gpu_launches"],
-                "roofline": main_res["roofline"], "cpu_baseline": cpu, "time_to_epsilon": main_res["time_to_epsilon"],
-                "delta_after_timed_steps": main_res["delta_after_timed_steps"],
-                "modes": "strict = bit-identical to the reference CPU path (default of the library); fast = MUFU "
-                         "ex2/lg2, the arithmetic of the reference's own GPU kernel, |du| <= 1e-5*|u| + 4e-7*iterations at matched epsilon",
-                "library": lib.epic_b200_version().decode()}
-        if other is not None:
-            line[other["math"] + "_mode"] = {k: other[k] for k in ("value", "ms_per_step", "e2e", "roofline", "clocks",
-                                                                   "gpu_launches")}
-        print(json.dumps(line), flush=True)
     if world > 1:
+        barrier()
         dist.destroy_process_group()
+    if rank != 0:
+        return      # the other ranks are done: rank 0 goes on alone with every GPU of the node
+    del u_pin, l_pin
+
+    gpu_base = None
+    if world == 1 and not args.no_gpu_baseline:
+        gpu_base = reference_gpu_baseline(args)
+    abi = None
+    if world > 1 and not args.no_abi_multi and size * layer_cells <= 2 ** 30:
+        try:
+            abi = abi_multi(args, world, updates_per_step)
+        except Exception as e:      # noqa: BLE001 -- the distributed numbers above stand on their own
+            abi = {"error": str(e)[:300]}
+
+    tte = main_res["time_to_epsilon"] or {}
+    skip = tte.get("with_static_tile_skipping") or {}
+    key = "%s | %s" % (workload_name(args), main_res["math"])
+    want = committed_fields().get(key)
+    line = {"metric": "Gcell-updates/s", "value": main_res["value"], "unit": "Gcell-updates/s", "n_gpus": world,
+            # compact keys first: what a scaling table needs besides `value`
+            "tte_s": tte.get("seconds"), "tte_skip_s": skip.get("seconds"), "tte_iterations": skip.get("iterations"),
+            "field_sha1": tte.get("field_sha1"),
+            "field_sha1_matches_n1": (None if want is None or tte.get("field_sha1") is None else
+                                      bool(want["field_sha1"] == tte["field_sha1"] and want["iterations"] == skip.get("iterations"))),
+            "roofline_frac": main_res["roofline"]["frac"], "e2e_value": main_res["e2e"]["value"],
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": main_res["ms_per_step"],
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": dict(workload(args), **main_res["config_extra"]),
+            "clocks": main_res["clocks"], "e2e": main_res["e2e"], "gpu_launches": main_res["gpu_launches"],
+            "roofline": main_res["roofline"], "cpu_baseline": cpu, "gpu_baseline": gpu_base, "abi_multi": abi,
+            "time_to_epsilon": main_res["time_to_epsilon"],
+            "delta_after_timed_steps": main_res["delta_after_timed_steps"],
+            "modes": "strict = bit-identical to the reference CPU path (default of the library; fields, deltas, iteration "
+                     "counts and streamlines equal harmonic_complete_cpu's bit for bit); fast = TOLERANCE mode: MUFU "
+                     "ex2/lg2, the arithmetic of the reference's own GPU kernel, |du| <= 1e-5*|u| + 4e-7*iterations at "
+                     "matched epsilon, streamlines within 0.05 cell but NOT cell-for-cell",
+            "library": lib.epic_b200_version().decode()}
+    if other is not None:
+        o_tte = other.get("time_to_epsilon") or {}
+        o_skip = o_tte.get("with_static_tile_skipping") or {}
+        line[other["math"] + "_mode"] = {k: other[k] for k in ("value", "ms_per_step", "e2e", "roofline", "clocks",
+                                                               "gpu_launches")}
+        line[other["math"] + "_mode"].update({"tte_skip_s": o_skip.get("seconds"), "tte_iterations": o_skip.get("iterations"),
+                                              "field_sha1": o_tte.get("field_sha1")})
+    print(json.dumps(line), flush=True)
+
+
+def abi_multi(args, world, updates_per_step):
+    """The same workload through the libepic C ABI alone, one process, EPIC_DEVICES naming all `world` GPUs: e2e
+    steps with host buffers, then harmonic_execute_gpu to epsilon (the device seconds of its loop come from the
+    library's statistics export; the ABI call itself also downloads the field)."""
+    import ctypes as ct
+
+    import torch
+
+    from epic_b200 import libepic
+    from epic_b200.harmonic import Harmonic
+    os.environ["EPIC_DEVICES"] = ",".join(str(i) for i in range(world))
+    os.environ["EPIC_MATH"] = args.math
+    u, locked = make_grid(args)
+    u_pin = torch.from_numpy(u).pin_memory()
+    l_pin = torch.from_numpy(locked.view(np.int32)).pin_memory()
+    del u, locked
+    u_host, l_host = u_pin.numpy(), l_pin.numpy().view(np.uint32)
+    u_keep = u_host.copy()
+    h = Harmonic(u_host, l_host, 1e-3, SWEEPS_PER_STEP)
+    h.initialize_gpu()
+    out = {"path": "libepic C ABI, single process, EPIC_DEVICES=%s (engine/grid.cu)" % os.environ["EPIC_DEVICES"],
+           "math": args.math}
+
+    def e2e_step():
+        h.currentIteration = 0
+        h.update_model_gpu()
+        h.run_iterations(SWEEPS_PER_STEP, "gpu")
+        h.get_potential_values_gpu()
+    u_host[:] = u_keep
+    e2e_step()
+    steps = 3
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        u_host[:] = u_keep
+        e2e_step()
+    dt = time.perf_counter() - t0
+    out["e2e"] = {"value": updates_per_step * steps / dt / 1e9, "unit": "Gcell-updates/s", "steps": steps,
+                  "ms_per_step": dt / steps * 1e3, "h2d_bytes_per_step": int(u_host.nbytes + l_host.nbytes),
+                  "d2h_bytes_per_step": int(u_host.nbytes),
+                  "note": "includes restoring the 1 GiB host array between steps (the ABI downloads into the caller's u)"}
+    # device-resident steps through the update / update_and_check calls
+    h.currentIteration = 1
+    h.run_iterations(SWEEPS_PER_STEP, "gpu")
+    t0 = time.perf_counter()
+    for _ in range(max(1, args.steps)):
+        h.run_iterations(SWEEPS_PER_STEP, "gpu")      # ends in a check sweep: synchronous
+    dt = time.perf_counter() - t0
+    out["value"] = updates_per_step * max(1, args.steps) / dt / 1e9
+    # to epsilon
+    u_host[:] = u_keep
+    h.currentIteration = 0
+    h.update_model_gpu()
+    t0 = time.perf_counter()
+    r = libepic.load().harmonic_execute_gpu(ct.byref(h), 1024)
+    wall = time.perf_counter() - t0
+    st = h.gpu_stats()
+    digests = band_digests(u_host, 0)
+    out["tte"] = {"return": int(r), "seconds": st["last_solve_seconds"], "execute_gpu_wall_seconds": wall,
+                  "iterations": int(h.currentIteration), "delta": float(h.delta), "slabs": st["slabs"],
+                  "tiles_skipped_by_slab": st["skipped_tiles"], "field_sha1": field_hash(digests)}
+    h.uninitialize_gpu()
+    return out
 
 
 def main():
@@ -440,11 +668,22 @@ def main():
     ap.add_argument("--tte", action="store_true", default=True,
                     help="also run to epsilon and report the time (default; twice: every tile swept / static tiles skipped)")
     ap.add_argument("--no-tte", dest="tte", action="store_false", help="skip the time-to-epsilon runs")
+    ap.add_argument("--no-tte-all-tiles", dest="tte_all_tiles", action="store_false", default=True,
+                    help="only the solve with static-tile skipping (halves the run time of the tte leg)")
+    ap.add_argument("--tte-both-modes", action="store_true", help="time-to-epsilon for the other arithmetic mode as well")
+    ap.add_argument("--workload", choices=["random", "maze"], default="random",
+                    help="random: BASELINE.json config 3 / 5 (random obstacles); maze: config 4 (procedural maze, use --size 65536 --gpus 8)")
+    ap.add_argument("--corridor", type=int, default=8, help="corridor width of the procedural maze")
+    ap.add_argument("--goals", type=int, default=None, help="goal cells (default 64 random-obstacle, 4 maze)")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the reference-GPU leg (N = 1)")
+    ap.add_argument("--no-abi-multi", action="store_true", help="skip the single-process EPIC_DEVICES leg (N > 1)")
     ap.add_argument("--tte-max-iterations", type=int, default=400000)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--halo", choices=["p2p", "nccl"], default="p2p", help="halo transport for --gpus > 1")
     ap.add_argument("--single-mode", action="store_true", help="measure only --math, not the other mode as well")
     args = ap.parse_args()
+    if args.goals is None:
+        args.goals = 64 if args.workload == "random" else 4
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
     if args.impl == "reference":
         run_reference(args)

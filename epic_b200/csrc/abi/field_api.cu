@@ -27,10 +27,13 @@ __global__ void selftest_math_kernel(uint32_t first, uint32_t count, uint32_t st
     epic_b200::StrictMath math;
     math.init(epic_b200::kLog4);
     math.bind(&tables);
+    // exp_nonpos is warp-synchronous (its table lookup is a shuffle): every lane evaluates, only the store is guarded
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const float x = __uint_as_float(first + (i < count ? i : 0u) * stride);
+    const float e = math.exp_nonpos(which == 0 ? x : 0.0f);
+    const float l = math.log_sum(which == 0 ? 1.0f : x);
     if (i < count) {
-        const float x = __uint_as_float(first + i * stride);
-        out[i] = which == 0 ? math.exp_nonpos(x) : math.log_sum(x);
+        out[i] = which == 0 ? e : l;
     }
 }
 

@@ -9,8 +9,8 @@
 // Device residency.  The reference keeps three raw cudaMalloc pointers (d_m, d_u, d_locked) plus
 // d_delta in the caller's struct; callers only zero-initialise them and hand the struct back
 // (src/epic_nav_core_plugin.cpp:67-70, src/epic_navigation_node_harmonic.cpp:70-73), so here all
-// four are handles to ONE `Context` that owns the Field (padded ping-pong buffers, 1-bit free mask,
-// stream, control block).  A handle is non-null exactly when the reference's pointer would be.
+// four are handles to ONE `Context` that owns the Grid (engine/grid.h: one Field per device named by
+// EPIC_DEVICES -- padded ping-pong buffers, 1-bit free mask, stream, control block -- a single one by default).  A handle is non-null exactly when the reference's pointer would be.
 // Contexts are kept in a registry, so a stale or foreign pointer is recognised and rejected with
 // EPIC_ERROR_INVALID_DATA instead of being dereferenced.
 //
@@ -24,22 +24,24 @@
 // device error codes, and the reference's callers then choose harmonic_complete_cpu themselves
 // (src/epic_nav_core_plugin.cpp:258-263).
 #include <stdio.h>
+#include <string.h>
 
 #include <mutex>
 #include <unordered_set>
 
 #include "../../../include/epic/libepic.h"
-#include "../engine/field.h"
+#include "../../../include/epic_b200.h"
+#include "../engine/grid.h"
 
-using epic_b200::Field;
 using epic_b200::FieldConfig;
+using epic_b200::Grid;
 
 namespace {
 
 enum { BIT_DIM = 1, BIT_U = 2, BIT_LOCKED = 4, BIT_DELTA = 8 };
 
 struct Context {
-    Field *field = nullptr;
+    Grid *field = nullptr;    // the grid on its device(s): one slab, or one per entry of EPIC_DEVICES
     unsigned n = 0;
     uint64_t m[3] = {0, 0, 0};
     unsigned live = 0;        // which of the four handles point here
@@ -117,7 +119,7 @@ int ensure_field(Context *c)
         return EPIC_SUCCESS;
     }
     const FieldConfig cfg = epic_b200::config_from_env();
-    return Field::create(&c->field, c->n, c->m, 0, c->m[0], 0, cfg);
+    return Grid::create(&c->field, c->n, c->m, cfg);
 }
 
 void release(Context *c, unsigned bit)
@@ -212,7 +214,7 @@ int harmonic_initialize_potential_values_gpu(Harmonic *harmonic)
         return (r == EPIC_ERROR_INVALID_DATA) ? r : EPIC_ERROR_DEVICE_MALLOC;
     }
     c->queued = 0;
-    r = c->field->upload_u(harmonic->u, 0, c->m[0]);
+    r = c->field->upload_u(harmonic->u);
     if (r != EPIC_SUCCESS) {
         complain(fn, "Failed to copy memory from host to device for the potential values.");
         if (c->live == 0) {
@@ -261,7 +263,7 @@ int harmonic_initialize_locked_gpu(Harmonic *harmonic)
     }
     r = issue_queued(c, true);
     if (r == EPIC_SUCCESS) {
-        r = c->field->upload_locked(harmonic->locked, 0, c->m[0]);
+        r = c->field->upload_locked(harmonic->locked);
     }
     if (r != EPIC_SUCCESS) {
         complain(fn, "Failed to copy memory from host to device for the locked cells.");
@@ -313,11 +315,11 @@ int harmonic_update_model_gpu(Harmonic *harmonic)
         return EPIC_ERROR_INVALID_DATA;
     }
     c->queued = 0;  // the field those sweeps would have produced is overwritten below
-    if (c->field->upload_u(harmonic->u, 0, c->m[0]) != EPIC_SUCCESS) {
+    if (c->field->upload_u(harmonic->u) != EPIC_SUCCESS) {
         complain(fn, "Failed to copy memory from host to device for the potential values.");
         return EPIC_ERROR_MEMCPY_TO_DEVICE;
     }
-    if (c->field->upload_locked(harmonic->locked, 0, c->m[0]) != EPIC_SUCCESS) {
+    if (c->field->upload_locked(harmonic->locked) != EPIC_SUCCESS) {
         complain(fn, "Failed to copy memory from host to device for the locked cells.");
         return EPIC_ERROR_MEMCPY_TO_DEVICE;
     }
@@ -436,7 +438,7 @@ int harmonic_get_potential_values_gpu(Harmonic *harmonic)
         complain(fn, "Invalid data.");
         return EPIC_ERROR_INVALID_DATA;
     }
-    if (issue_queued(c, true) != EPIC_SUCCESS || c->field->download_u(harmonic->u, 0, c->m[0]) != EPIC_SUCCESS) {
+    if (issue_queued(c, true) != EPIC_SUCCESS || c->field->download_u(harmonic->u) != EPIC_SUCCESS) {
         complain(fn, "Failed to copy memory from device to host for the potential values.");
         return EPIC_ERROR_MEMCPY_TO_HOST;
     }
@@ -461,8 +463,13 @@ int harmonic_execute_gpu(Harmonic *harmonic, unsigned int numThreads)
         complain(fn, "Invalid data.");
         return EPIC_ERROR_INVALID_DATA;
     }
+    // Sweeps queued by earlier harmonic_update_gpu calls have already been applied to d_u in the reference
+    // (execute restarts the iteration count, not the field): issue them before the solve starts from them.
+    if (issue_queued(c, true) != EPIC_SUCCESS) {
+        complain(fn, "Failed to execute the 'Gauss-Seidel update' kernel.");
+        return EPIC_ERROR_KERNEL_EXECUTION;
+    }
     harmonic->currentIteration = 0;
-    c->queued = 0;
 
     int result = harmonic_initialize_gpu(harmonic, numThreads);
     if (result != EPIC_SUCCESS) {
@@ -578,7 +585,7 @@ int harmonic_utilities_set_occupancy_grid_2d_gpu(Harmonic *harmonic, const signe
     }
     int r = issue_queued(c, true);
     if (r == EPIC_SUCCESS) {
-        r = c->field->ingest_occupancy_2d(data, 0, c->m[0], obstacleThreshold, noChangeValue);
+        r = c->field->ingest_occupancy_2d(data, obstacleThreshold, noChangeValue);
     }
     if (r != EPIC_SUCCESS) {
         complain(fn, "Failed to classify the occupancy grid on the device.");
@@ -716,3 +723,25 @@ int harmonic_compute_path_poses_2d_gpu(Harmonic *harmonic, float x, float y, flo
 }
 
 }  // namespace epic
+
+extern "C" int epic_b200_harmonic_stats(const void *harmonic, epic_b200_stats *out)
+{
+    if (harmonic == nullptr || out == nullptr) {
+        return EPIC_ERROR_INVALID_DATA;
+    }
+    Context *c = find_context((const epic::Harmonic *)harmonic);
+    if (c == nullptr || c->field == nullptr) {
+        return EPIC_ERROR_INVALID_DATA;
+    }
+    const epic_b200::GridStats s = c->field->stats();
+    memset(out, 0, sizeof(*out));
+    out->slabs = s.slabs;
+    out->last_solve_iterations = s.last_solve_iterations;
+    out->last_solve_delta = s.last_solve_delta;
+    out->last_solve_seconds = s.last_solve_seconds;
+    out->launches = s.launches;
+    for (uint32_t i = 0; i < s.slabs && i < 16; ++i) {
+        out->skipped_tiles[i] = s.skipped_by_slab[i];
+    }
+    return EPIC_SUCCESS;
+}

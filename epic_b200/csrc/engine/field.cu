@@ -86,6 +86,13 @@ struct DeviceGuard {
 
 uint64_t round_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
 
+FieldView2D empty_view()
+{
+    FieldView2D f;
+    memset(&f, 0, sizeof(f));
+    return f;
+}
+
 template <class K>
 bool allow_smem(K kernel, size_t bytes)
 {
@@ -129,6 +136,36 @@ FieldConfig config_from_env()
     }
     if (const char *s = getenv("EPIC_DEVICE")) {
         cfg.device = atoi(s);
+    }
+    if (const char *s = getenv("EPIC_DEVICES")) {
+        int have = 0;
+        cudaGetDeviceCount(&have);
+        cudaGetLastError();
+        if (strcmp(s, "all") == 0) {
+            for (int i = 0; i < have && i < kMaxSlabs; ++i) {
+                cfg.devices[cfg.ndevices++] = i;
+            }
+        } else if (strchr(s, ',') == nullptr) {
+            const int n = atoi(s);                 // a count: the first n devices (one specific device: EPIC_DEVICE)
+            for (int i = 0; i < n && i < have && i < kMaxSlabs; ++i) {
+                cfg.devices[cfg.ndevices++] = i;
+            }
+        } else {
+            const char *q = s;
+            while (*q != 0 && cfg.ndevices < kMaxSlabs) {
+                char *end = nullptr;
+                const long d = strtol(q, &end, 10);
+                if (end == q) {
+                    break;
+                }
+                if (d >= 0 && d < have) {
+                    cfg.devices[cfg.ndevices++] = (int)d;
+                } else {
+                    fprintf(stderr, "Warning[epic_b200]: EPIC_DEVICES names device %ld, which does not exist; ignored.\n", d);
+                }
+                q = (*end == ',') ? end + 1 : end;
+            }
+        }
     }
     return cfg;
 }
@@ -1061,6 +1098,19 @@ int Field::solve(float epsilon, uint32_t stagger, uint32_t m_max, uint32_t *iter
         explicit Tracking(bool &f) : flag(f), before(f) { flag = true; }
         ~Tracking() { flag = before; }
     } tracking(tracking_);
+    struct ClearCtrl {  // an early error return must not leave `done` set: later run() calls would silently do nothing
+        Field *f;
+        bool armed = true;
+        ~ClearCtrl()
+        {
+            if (armed) {
+                cudaStreamSynchronize(f->stream_);
+                cudaMemsetAsync(f->ctrl_, 0, sizeof(Ctrl), f->stream_);
+                cudaStreamSynchronize(f->stream_);
+                cudaGetLastError();
+            }
+        }
+    } clear_ctrl{this};
     if (cudaMemsetAsync(ctrl_, 0, sizeof(Ctrl), stream_) != cudaSuccess) {
         cudaGetLastError();
         return kMemcpyToDevice;
@@ -1118,7 +1168,139 @@ int Field::solve(float epsilon, uint32_t stagger, uint32_t m_max, uint32_t *iter
     skipped_tiles_ += fin->skipped;
     *iteration = fin->final_iteration;
     *delta = fin->last_delta;
+    clear_ctrl.armed = false;
     // leave the flag clear so that later update / update_and_check calls sweep again
+    if (cudaMemsetAsync(ctrl_, 0, sizeof(Ctrl), stream_) != cudaSuccess || cudaStreamSynchronize(stream_) != cudaSuccess) {
+        cudaGetLastError();
+        return kDeviceSynchronize;
+    }
+    return kSuccess;
+}
+
+static_assert(kViewSlabs >= kMaxSlabs && kDecideSlots >= kMaxSlabs, "a Grid's slabs must fit the device-side tables");
+
+static FieldView2D grid_view(const std::vector<Field *> &slabs, void (Field::*add)(FieldView2D *) const)
+{
+    FieldView2D view = empty_view();
+    for (const Field *f : slabs) {
+        (f->*add)(&view);
+    }
+    return view;
+}
+
+int Field::potential_grid(const std::vector<Field *> &slabs, float x, float y, float *value)
+{
+    return potential_view(grid_view(slabs, &Field::add_to_view), x, y, value);
+}
+
+int Field::gradient_grid(const std::vector<Field *> &slabs, float x, float y, float cd, float *px, float *py)
+{
+    return gradient_view(grid_view(slabs, &Field::add_to_view), x, y, cd, px, py);
+}
+
+int Field::paths_grid(const std::vector<Field *> &slabs, uint32_t count, const float *starts, float step, float cd,
+                      uint32_t max_length, int *ret, uint32_t *k, float **paths)
+{
+    return paths_view(grid_view(slabs, &Field::add_to_view), count, starts, step, cd, max_length, ret, k, paths);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Hooks for Grid::solve (a grid sharded over several slabs of this process)
+
+int Field::default_sweeps_per_pass(unsigned n, const FieldConfig &cfg)
+{
+    if (n != 2) {
+        return k3HR;
+    }
+    return cfg.sweeps_per_pass > 0 ? std::min(cfg.sweeps_per_pass, 8) : 4;
+}
+
+int Field::solve_begin(float epsilon, uint32_t m_max)
+{
+    DeviceGuard guard(cfg_.device);
+    if (cudaMemsetAsync(ctrl_, 0, sizeof(Ctrl), stream_) != cudaSuccess) {
+        cudaGetLastError();
+        return kMemcpyToDevice;
+    }
+    set_rule_kernel<<<1, 1, 0, stream_>>>(ctrl_, epsilon, m_max);
+    launches_++;
+    return cudaGetLastError() == cudaSuccess ? kSuccess : kKernelExecution;
+}
+
+static DecideAllParams decide_params(Ctrl *ctrl, const DecideWiring &w, uint32_t tag, uint32_t count, uint32_t buffer, bool rule)
+{
+    DecideAllParams p;
+    memset(&p, 0, sizeof(p));
+    p.ctrl = ctrl;
+    p.inbox = w.inbox[w.me];
+    for (uint32_t i = 0; i < w.nslabs; ++i) {
+        p.peer_inbox[i] = w.inbox[i];
+    }
+    p.nslabs = w.nslabs;
+    p.me = w.me;
+    p.tag = tag;
+    p.count = count;
+    p.buffer = buffer;
+    p.use_ctrl_rule = rule ? 1u : 0u;
+    return p;
+}
+
+int Field::publish_delta(const DecideWiring &w, uint32_t tag)
+{
+    DeviceGuard guard(cfg_.device);
+    publish_delta_kernel<<<1, 32, 0, stream_>>>(decide_params(ctrl_, w, tag, 0, (uint32_t)cur_, true));
+    launches_++;
+    return cudaGetLastError() == cudaSuccess ? kSuccess : kKernelExecution;
+}
+
+int Field::decide_all(const DecideWiring &w, uint32_t tag, uint32_t count, bool rule)
+{
+    DeviceGuard guard(cfg_.device);
+    decide_all_kernel<<<1, 32, 0, stream_>>>(decide_params(ctrl_, w, tag, count, (uint32_t)cur_, rule));
+    launches_++;
+    return cudaGetLastError() == cudaSuccess ? kSuccess : kKernelExecution;
+}
+
+int Field::snapshot(int slot)
+{
+    DeviceGuard guard(cfg_.device);
+    if (cudaMemcpyAsync(&ctrl_host_[slot], ctrl_, sizeof(Ctrl), cudaMemcpyDeviceToHost, stream_) != cudaSuccess ||
+        cudaEventRecord(events_[slot], stream_) != cudaSuccess) {
+        cudaGetLastError();
+        return kMemcpyToHost;
+    }
+    return kSuccess;
+}
+
+int Field::wait_snapshot(int slot, SolveSnapshot *out)
+{
+    DeviceGuard guard(cfg_.device);
+    if (cudaEventSynchronize(events_[slot]) != cudaSuccess) {
+        cudaGetLastError();
+        return kDeviceSynchronize;
+    }
+    const Ctrl &c = ctrl_host_[slot];
+    out->done = c.done;
+    out->final_iteration = c.final_iteration;
+    out->final_buffer = c.final_buffer;
+    out->skipped = c.skipped;
+    out->failed = c.failed;
+    out->last_delta = c.last_delta;
+    return kSuccess;
+}
+
+int Field::solve_end(const SolveSnapshot &fin)
+{
+    DeviceGuard guard(cfg_.device);
+    // this slab's own count of skipped tiles (the decision fields are the same on every slab)
+    if (cudaMemcpyAsync(&ctrl_host_[0], ctrl_, sizeof(Ctrl), cudaMemcpyDeviceToHost, stream_) != cudaSuccess ||
+        cudaStreamSynchronize(stream_) != cudaSuccess) {
+        cudaGetLastError();
+        return kDeviceSynchronize;
+    }
+    skipped_tiles_ += ctrl_host_[0].skipped;
+    cur_ = (int)fin.final_buffer;
+    chg_stale_ = true;
     if (cudaMemsetAsync(ctrl_, 0, sizeof(Ctrl), stream_) != cudaSuccess || cudaStreamSynchronize(stream_) != cudaSuccess) {
         cudaGetLastError();
         return kDeviceSynchronize;
@@ -1252,25 +1434,35 @@ int Field::reset_free_cells_2d()
 // ------------------------------------------------------------------------------------------------
 // Streamlines
 
-static FieldView2D make_view(const float *u, const uint32_t *mask, uint64_t pitch, uint64_t mask_wpr,
-                             const uint64_t *gm, int64_t grow0)
+void Field::add_to_view(FieldView2D *view) const
 {
-    FieldView2D f;
-    f.u = u;
-    f.mask = mask;
-    f.pitch = pitch;
-    f.mask_wpr = (uint32_t)mask_wpr;
-    f.m0 = (uint32_t)gm[0];
-    f.m1 = (uint32_t)gm[1];
-    f.grow0 = grow0;
-    return f;
+    FieldView2D &f = *view;
+    if (f.nslabs == 0) {
+        f.pitch = pitch_;
+        f.mask_wpr = (uint32_t)mask_wpr_;
+        f.m0 = (uint32_t)gm_[0];
+        f.m1 = (uint32_t)gm_[1];
+    }
+    const uint32_t i = f.nslabs++;
+    f.u[i] = u_[cur_];
+    f.mask[i] = freemask_;
+    f.grow0[i] = grow0_;
+    f.row_end[i] = (uint32_t)(row0_ + rows_);
 }
+
 
 int Field::potential_2d(float x, float y, float *value)
 {
     if (n_ != 2 || value == nullptr || rows_ != gm_[0]) {
         return kInvalidData;
     }
+    FieldView2D view = empty_view();
+    add_to_view(&view);
+    return potential_view(view, x, y, value);
+}
+
+int Field::potential_view(const FieldView2D &view, float x, float y, float *value)
+{
     DeviceGuard guard(cfg_.device);
     int r = ensure_staging(&staging_, &staging_bytes_, 64);
     if (r != kSuccess) {
@@ -1278,8 +1470,7 @@ int Field::potential_2d(float x, float y, float *value)
     }
     float *d_out = (float *)staging_;
     int *d_ret = (int *)(d_out + 2);
-    potential_gradient_kernel<<<1, 1, 0, stream_>>>(make_view(u_[cur_], freemask_, pitch_, mask_wpr_, gm_, grow0_), x, y,
-                                                    0.0f, 0, d_out, d_ret);
+    potential_gradient_kernel<<<1, 1, 0, stream_>>>(view, x, y, 0.0f, 0, d_out, d_ret);
     launches_++;
     float h[3];
     if (cudaGetLastError() != cudaSuccess) {
@@ -1303,6 +1494,13 @@ int Field::gradient_2d(float x, float y, float cd, float *px, float *py)
     if (n_ != 2 || px == nullptr || py == nullptr || rows_ != gm_[0]) {
         return kInvalidData;
     }
+    FieldView2D view = empty_view();
+    add_to_view(&view);
+    return gradient_view(view, x, y, cd, px, py);
+}
+
+int Field::gradient_view(const FieldView2D &view, float x, float y, float cd, float *px, float *py)
+{
     DeviceGuard guard(cfg_.device);
     int r = ensure_staging(&staging_, &staging_bytes_, 64);
     if (r != kSuccess) {
@@ -1310,8 +1508,7 @@ int Field::gradient_2d(float x, float y, float cd, float *px, float *py)
     }
     float *d_out = (float *)staging_;
     int *d_ret = (int *)(d_out + 2);
-    potential_gradient_kernel<<<1, 1, 0, stream_>>>(make_view(u_[cur_], freemask_, pitch_, mask_wpr_, gm_, grow0_), x, y,
-                                                    cd, 1, d_out, d_ret);
+    potential_gradient_kernel<<<1, 1, 0, stream_>>>(view, x, y, cd, 1, d_out, d_ret);
     launches_++;
     float h[3];
     if (cudaGetLastError() != cudaSuccess) {
@@ -1338,6 +1535,14 @@ int Field::paths_2d(uint32_t count, const float *starts, float step, float cd, u
         rows_ != gm_[0]) {
         return kInvalidData;
     }
+    FieldView2D view = empty_view();
+    add_to_view(&view);
+    return paths_view(view, count, starts, step, cd, max_length, ret, k, paths);
+}
+
+int Field::paths_view(const FieldView2D &view, uint32_t count, const float *starts, float step, float cd,
+                      uint32_t max_length, int *ret, uint32_t *k, float **paths)
+{
     DeviceGuard guard(cfg_.device);
     // chunk: points emitted per path and launch
     const uint32_t chunk = (uint32_t)std::max<uint64_t>(256, std::min<uint64_t>(65536, (32ull << 20) / ((uint64_t)count * 8)));
@@ -1367,11 +1572,10 @@ int Field::paths_2d(uint32_t count, const float *starts, float step, float cd, u
         cudaGetLastError();
         result = kMemcpyToDevice;
     }
-    const FieldView2D view = make_view(u_[cur_], freemask_, pitch_, mask_wpr_, gm_, grow0_);
     bool running = true;
     for (uint32_t launch = 0; running && result == kSuccess; ++launch) {
-        path_2d_kernel<<<(count + 31) / 32, 32, 0, stream_>>>(view, count, d_starts, step, cd, max_floats, chunk,
-                                                              d_states, d_out, d_emitted, launch == 0 ? 1u : 0u);
+        path_2d_kernel<<<(count + kPathWarps - 1) / kPathWarps, 32 * kPathWarps, 0, stream_>>>(
+            view, count, d_starts, step, cd, max_floats, chunk, d_states, d_out, d_emitted, launch == 0 ? 1u : 0u);
         launches_++;
         if (cudaGetLastError() != cudaSuccess) {
             result = kKernelExecution;

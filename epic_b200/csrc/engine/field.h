@@ -23,14 +23,21 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <vector>
+
 namespace epic_b200 {
 
 enum MathMode { MATH_STRICT = 0, MATH_FAST = 1 };
 
 struct Ctrl;
+struct FieldView2D;
+
+constexpr int kMaxSlabs = 16;   // slabs of one grid held by one process (Grid, grid.h)
 
 struct FieldConfig {
     int device = -1;          // -1 = the current device
+    int ndevices = 0;         // EPIC_DEVICES: the devices a whole grid is sharded over by the libepic ABI (Grid);
+    int devices[kMaxSlabs] = {0};   // 0 = not set (one slab on `device`).  An ordinal may repeat (several slabs on one GPU).
     MathMode math = MATH_STRICT;
     int sweeps_per_pass = 0;  // T; 0 = default
     int tile_rows = 0;        // 2-D: rows of the shared-memory tile (incl. halo); 0 = by grid size
@@ -51,8 +58,22 @@ struct PeerInfo {
     int32_t device;
 };
 
+// How the slabs of one Grid find each other's inboxes for the all-reduce of the convergence check
+// (decide_all_kernel, aux_kernels.cuh), and what the host reads back of a slab's control block.
+struct DecideWiring {
+    unsigned long long *inbox[kMaxSlabs];
+    uint32_t nslabs = 0, me = 0;
+};
+struct SolveSnapshot {
+    uint32_t done = 0, final_iteration = 0, final_buffer = 0, skipped = 0, failed = 0;
+    float last_delta = 0.0f;
+};
+
 // Return codes are the reference's (libepic/include/epic/error_codes.h:31-46).
+class Grid;
+
 class Field {
+    friend class Grid;
 public:
     // n = 2 or 3; gm = global dimensions; this slab owns x0 in [row0, row0+rows).
     // `ghost` x0-layers are kept on each side for neighbouring slabs (0 for a whole grid).
@@ -132,6 +153,28 @@ public:
 
 private:
     Field() {}
+    // The streamline entry points on an explicit view of the field: a Grid passes the slabs of all its devices
+    // (add_to_view appends this slab), the kernels run on this slab's device and read the others over NVLink.
+    void add_to_view(FieldView2D *view) const;
+    int potential_view(const FieldView2D &view, float x, float y, float *value);
+    int gradient_view(const FieldView2D &view, float x, float y, float cd, float *px, float *py);
+    int paths_view(const FieldView2D &view, uint32_t count, const float *starts, float step, float cd,
+                   uint32_t max_length, int *ret, uint32_t *k, float **paths);
+    // The same on the slabs of a whole Grid (this = the slab whose device runs the kernels).
+    int potential_grid(const std::vector<Field *> &slabs, float x, float y, float *value);
+    int gradient_grid(const std::vector<Field *> &slabs, float x, float y, float cd, float *px, float *py);
+    int paths_grid(const std::vector<Field *> &slabs, uint32_t count, const float *starts, float step, float cd,
+                   uint32_t max_length, int *ret, uint32_t *k, float **paths);
+    // Pieces of the solve loop a Grid drives on each of its slabs (grid.cu): arm the device-side termination
+    // rule; after a check sweep publish this slab's delta to every slab and decide on the maximum; copy the
+    // control block to pinned slot `slot` / wait for that copy; adopt the final state.
+    int solve_begin(float epsilon, uint32_t m_max);
+    int publish_delta(const DecideWiring &w, uint32_t tag);
+    int decide_all(const DecideWiring &w, uint32_t tag, uint32_t count, bool rule);
+    int snapshot(int slot);
+    int wait_snapshot(int slot, SolveSnapshot *out);
+    int solve_end(const SolveSnapshot &fin);
+    static int default_sweeps_per_pass(unsigned n, const FieldConfig &cfg);
     // Layers allocated per buffer: padded so that a TMA box never exceeds the tensor it reads from.
     uint64_t alloc_layers() const
     {
@@ -218,7 +261,8 @@ private:
     void close_peers();
 };
 
-// Parses EPIC_MATH (strict|fast), EPIC_SWEEPS_PER_PASS, EPIC_TILE_ROWS, EPIC_THREADS, EPIC_DEVICE.
+// Parses EPIC_MATH (strict|fast), EPIC_SWEEPS_PER_PASS, EPIC_TILE_ROWS, EPIC_THREADS, EPIC_DEVICE and
+// EPIC_DEVICES ("0,1,2,3", "all", or a count "4" = the first four devices).
 FieldConfig config_from_env();
 
 }  // namespace epic_b200

@@ -31,6 +31,7 @@ struct Ctrl {                      // device-resident control block
     uint32_t m_max;                // ... and currentIteration >= m_max
     uint32_t skipped;              // tiles that returned early as static since the counter was last taken
     uint32_t taken_skipped;        // take_delta_kernel moves `skipped` here for the host to read
+    uint32_t failed;               // decide_all_kernel gave up waiting for another slab of the grid
 };
 
 // One warp packs 32 consecutive cells of one row into one mask word (ballot), coalesced reads.
@@ -214,16 +215,118 @@ __global__ void take_delta_kernel(Ctrl *ctrl, uint32_t it_after)
     ctrl->skipped = 0u;
 }
 
+// The termination rule for a grid that is sharded over several slabs of ONE process (engine/grid.cu): an
+// all-reduce(max) of the slabs' deltas done by the decision kernels themselves over NVLink peer memory, so that
+// the host never has to gather deltas and can keep queueing solver periods ahead of the device (as it does for a
+// single slab).  Every slab has an inbox of 2 x kDecideSlots 64-bit words; slab `me` stores {period tag, delta
+// bits} into word [tag & 1][me] of EVERY slab's inbox (one atomic 8-byte store each, system-scope release), then
+// waits until its own inbox holds this period's tag from every slab and applies the rule to the maximum.  All
+// slabs see the same deltas, so all reach the same decision for the same period.  Two parities suffice: a slab
+// can publish period k + 2 only after every slab published k + 1, i.e. after every slab finished reading k.
+constexpr int kDecideSlots = 16;
+
+struct DecideAllParams {
+    Ctrl *ctrl;
+    unsigned long long *inbox;                      // this slab's inbox
+    unsigned long long *peer_inbox[kDecideSlots];   // every slab's inbox (this slab's own included)
+    uint32_t nslabs, me;
+    uint32_t tag;                                   // 1-based period index over the grid's lifetime
+    uint32_t count;                                 // half-sweeps in this period
+    uint32_t buffer;                                // ping-pong buffer the period ends in
+    uint32_t use_ctrl_rule;                         // 1: epsilon / m_max / iteration from ctrl (solve); 0: only publish
+                                                    //    the global delta in ctrl->last_delta (update_and_check)
+};
+
+// First half: store {tag, my delta} into every slab's inbox.  A separate kernel from the wait below so that slabs
+// sharing one stream (several slabs on one device) can all publish before the first of them waits.
+__global__ void publish_delta_kernel(DecideAllParams p)
+{
+    const uint32_t lane = threadIdx.x;
+    if (p.use_ctrl_rule && p.ctrl->done) {
+        return;     // every slab decided "done" in the same period: nobody publishes, nobody waits
+    }
+    const uint32_t mine = p.ctrl->delta_bits;
+    const uint32_t slot = (p.tag & 1u) * kDecideSlots;
+    if (lane < p.nslabs) {
+        const unsigned long long word = ((unsigned long long)p.tag << 32) | mine;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p.peer_inbox[lane] + slot + p.me), "l"(word) : "memory");
+    }
+}
+
+__global__ void decide_all_kernel(DecideAllParams p)
+{
+    const uint32_t lane = threadIdx.x;
+    if (p.use_ctrl_rule && p.ctrl->done) {
+        return;
+    }
+    const uint32_t slot = (p.tag & 1u) * kDecideSlots;
+    uint32_t bits = 0u;
+    bool late = false;
+    if (lane < p.nslabs) {
+        unsigned long long w, t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(p.inbox + slot + lane) : "memory");
+            if ((uint32_t)(w >> 32) != p.tag) {
+                __nanosleep(200);
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                late = (t1 - t0) > 30000000000ull;     // 30 s: a slab of this grid died; give up instead of hanging
+            }
+        } while ((uint32_t)(w >> 32) != p.tag && !late);
+        bits = (uint32_t)w;
+    }
+    const bool failed = __any_sync(0xffffffffu, late);
+    for (int o = 16; o > 0; o >>= 1) {       // deltas are non-negative floats: their bit patterns order like integers
+        bits = max(bits, __shfl_xor_sync(0xffffffffu, bits, o));
+    }
+    if (lane != 0) {
+        return;
+    }
+    Ctrl *ctrl = p.ctrl;
+    const float delta = __uint_as_float(bits);
+    ctrl->delta_bits = 0u;
+    ctrl->last_delta = delta;
+    if (failed) {
+        ctrl->failed = 1u;
+        ctrl->final_buffer = p.buffer;
+        __threadfence();
+        ctrl->done = 1u;
+        return;
+    }
+    if (!p.use_ctrl_rule) {
+        ctrl->taken_skipped = ctrl->skipped;
+        ctrl->skipped = 0u;
+        return;
+    }
+    const uint32_t it_after = ctrl->iteration + p.count;
+    ctrl->last_check_iteration = it_after;
+    ctrl->iteration = it_after;
+    ctrl->checks += 1u;
+    if (delta < ctrl->epsilon && it_after >= ctrl->m_max) {
+        ctrl->final_iteration = it_after;
+        ctrl->final_buffer = p.buffer;
+        __threadfence();
+        ctrl->done = 1u;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Streamlines
 
+// The device-resident field as the streamline kernels see it: one entry per slab (one for a whole-grid field).
+// Slab i holds the authoritative copy of global rows [row_end[i-1], row_end[i]); slabs of a sharded grid may
+// live on other GPUs of the node, in which case their rows are read over NVLink (peer access).
+constexpr int kViewSlabs = 16;
+
 struct FieldView2D {
-    const float *u;        // current buffer, buffer-row 0
-    const uint32_t *mask;  // free bits, buffer layout
+    const float *u[kViewSlabs];        // current buffer of slab i, buffer-row 0
+    const uint32_t *mask[kViewSlabs];  // free bits, buffer layout
+    int64_t grow0[kViewSlabs];         // global row of buffer row 0 (0 for a whole-grid field)
+    uint32_t row_end[kViewSlabs];      // first global row NOT owned by slab i
+    uint32_t nslabs;
     uint64_t pitch;
     uint32_t mask_wpr;
-    uint32_t m0, m1;       // global dimensions
-    int64_t grow0;         // global row of buffer row 0 (0 for a whole-grid field)
+    uint32_t m0, m1;                   // global dimensions
 };
 
 enum { kPathOk = 0, kPathInvalidLocation = 10, kPathInvalidGradient = 12, kPathInvalidPath = 13 };
@@ -234,53 +337,100 @@ __device__ __forceinline__ uint32_t f2u_x86(float f)
     return (uint32_t)(uint64_t)__float2ll_rz(f);
 }
 
-__device__ __forceinline__ bool cell_locked(const FieldView2D &f, uint32_t xc, uint32_t yc)
+__device__ __forceinline__ uint32_t slab_of(const FieldView2D &f, uint32_t yc)
 {
-    const uint64_t b = (uint64_t)((int64_t)yc - f.grow0);
-    return ((__ldg(f.mask + b * f.mask_wpr + (xc >> 5)) >> (xc & 31u)) & 1u) == 0u;
+    uint32_t i = 0;
+    while (i + 1u < f.nslabs && yc >= f.row_end[i]) {
+        ++i;
+    }
+    return i;
+}
+
+// Loads for cell (xc, yc), which must lie inside the grid.
+__device__ __forceinline__ uint32_t cell_mask_word(const FieldView2D &f, uint32_t xc, uint32_t yc)
+{
+    const uint32_t s = slab_of(f, yc);
+    const uint64_t b = (uint64_t)((int64_t)yc - f.grow0[s]);
+    return __ldg(f.mask[s] + b * f.mask_wpr + (xc >> 5));
 }
 
 __device__ __forceinline__ float cell_u(const FieldView2D &f, uint32_t xc, uint32_t yc)
 {
-    const uint64_t b = (uint64_t)((int64_t)yc - f.grow0);
-    return __ldg(f.u + b * f.pitch + xc);
+    const uint32_t s = slab_of(f, yc);
+    const uint64_t b = (uint64_t)((int64_t)yc - f.grow0[s]);
+    return __ldg(f.u[s] + b * f.pitch + xc);
 }
 
-// harmonic_path_cpu.cpp:52-58 / :168-175: outside the grid, or an obstacle (locked and negative).
-__device__ __forceinline__ bool cell_blocked(const FieldView2D &f, uint32_t xc, uint32_t yc)
+// Everything one bilinear potential lookup (harmonic_path_cpu.cpp:41-82) reads, fetched with INDEPENDENT loads
+// issued back to back (out-of-range cells are not read): a streamline is a chain of dependent steps, so what
+// matters is the number of memory round trips per step, not the number of loads.
+struct PotentialTaps {
+    uint32_t xl, xr, yt, yb;       // the four cell indices
+    bool centre_in, taps_in;
+    uint32_t centre_word;          // mask word of the cell the point rounds to
+    float centre_u;
+    float tl, tr, bl, br;
+    float x, y;
+};
+
+__device__ __forceinline__ void potential_fetch(const FieldView2D &f, float x, float y, PotentialTaps &t)
 {
-    if (xc >= f.m1 || yc >= f.m0) {
-        return true;
+    t.x = x;
+    t.y = y;
+    t.xl = f2u_x86(__fsub_rn(x, 0.5f));
+    t.xr = f2u_x86(__fadd_rn(x, 0.5f));
+    t.yt = f2u_x86(__fsub_rn(y, 0.5f));
+    t.yb = f2u_x86(__fadd_rn(y, 0.5f));
+    t.centre_in = t.xr < f.m1 && t.yb < f.m0;                 // the centre cell is (xr, yb): (unsigned)(x + 0.5f)
+    t.taps_in = t.centre_in && t.xl < f.m1 && t.yt < f.m0;
+    t.centre_word = 0u;
+    t.centre_u = 0.0f;
+    t.tl = t.tr = t.bl = t.br = 0.0f;
+    if (t.centre_in) {
+        t.centre_word = cell_mask_word(f, t.xr, t.yb);
+        t.centre_u = cell_u(f, t.xr, t.yb);
     }
-    return cell_locked(f, xc, yc) && cell_u(f, xc, yc) < 0.0f;
+    if (t.taps_in) {
+        t.tl = cell_u(f, t.xl, t.yt);
+        t.tr = cell_u(f, t.xr, t.yt);
+        t.bl = cell_u(f, t.xl, t.yb);
+        t.br = t.centre_u;
+    }
 }
 
-__device__ int potential_2d(const FieldView2D &f, float x, float y, float *out)
+// harmonic_path_cpu.cpp:52-58: outside the grid, or an obstacle (locked and negative) -> invalid location;
+// otherwise the bilinear blend with separate multiplies and adds (:60-79).
+__device__ __forceinline__ int potential_eval(const PotentialTaps &t, float *out)
 {
-    if (cell_blocked(f, f2u_x86(__fadd_rn(x, 0.5f)), f2u_x86(__fadd_rn(y, 0.5f)))) {
+    if (!t.centre_in) {
         return kPathInvalidLocation;
     }
-    const uint32_t xl = f2u_x86(__fsub_rn(x, 0.5f)), xr = f2u_x86(__fadd_rn(x, 0.5f));
-    const uint32_t yt = f2u_x86(__fsub_rn(y, 0.5f)), yb = f2u_x86(__fadd_rn(y, 0.5f));
-    if (xl >= f.m1 || xr >= f.m1 || yt >= f.m0 || yb >= f.m0) {
+    const bool locked = ((t.centre_word >> (t.xr & 31u)) & 1u) == 0u;
+    if (locked && t.centre_u < 0.0f) {
+        return kPathInvalidLocation;
+    }
+    if (!t.taps_in) {
         return kPathInvalidLocation;  // the reference would read outside the arrays here
     }
-    const float alpha = __fsub_rn(x, (float)xl);
-    const float beta = __fsub_rn(y, (float)yt);
+    const float alpha = __fsub_rn(t.x, (float)t.xl);
+    const float beta = __fsub_rn(t.y, (float)t.yt);
     const float na = __fsub_rn(1.0f, alpha), nb = __fsub_rn(1.0f, beta);
-    const float one = __fadd_rn(__fmul_rn(na, cell_u(f, xl, yt)), __fmul_rn(alpha, cell_u(f, xr, yt)));
-    const float two = __fadd_rn(__fmul_rn(na, cell_u(f, xl, yb)), __fmul_rn(alpha, cell_u(f, xr, yb)));
+    const float one = __fadd_rn(__fmul_rn(na, t.tl), __fmul_rn(alpha, t.tr));
+    const float two = __fadd_rn(__fmul_rn(na, t.bl), __fmul_rn(alpha, t.br));
     *out = __fadd_rn(__fmul_rn(nb, one), __fmul_rn(beta, two));
     return kPathOk;
 }
 
-__device__ int gradient_2d(const FieldView2D &f, float x, float y, float cd, float *px, float *py)
+__device__ int potential_2d(const FieldView2D &f, float x, float y, float *out)
 {
-    float v0 = 0.0f, v1 = 0.0f, v2 = 0.0f, v3 = 0.0f;
-    int r = potential_2d(f, __fsub_rn(x, cd), y, &v0);
-    r += potential_2d(f, __fadd_rn(x, cd), y, &v1);
-    r += potential_2d(f, x, __fsub_rn(y, cd), &v2);
-    r += potential_2d(f, x, __fadd_rn(y, cd), &v3);
+    PotentialTaps t;
+    potential_fetch(f, x, y, t);
+    return potential_eval(t, out);
+}
+
+// harmonic_path_cpu.cpp:85-118 from four potentials (any failure -> invalid gradient).
+__device__ __forceinline__ int gradient_from(int r, float v0, float v1, float v2, float v3, float cd, float *px, float *py)
+{
     if (r != kPathOk) {
         return kPathInvalidGradient;
     }
@@ -294,6 +444,21 @@ __device__ int gradient_2d(const FieldView2D &f, float x, float y, float cd, flo
     return kPathOk;
 }
 
+__device__ int gradient_2d(const FieldView2D &f, float x, float y, float cd, float *px, float *py)
+{
+    PotentialTaps t0, t1, t2, t3;
+    potential_fetch(f, __fsub_rn(x, cd), y, t0);
+    potential_fetch(f, __fadd_rn(x, cd), y, t1);
+    potential_fetch(f, x, __fsub_rn(y, cd), t2);
+    potential_fetch(f, x, __fadd_rn(y, cd), t3);
+    float v0 = 0.0f, v1 = 0.0f, v2 = 0.0f, v3 = 0.0f;
+    int r = potential_eval(t0, &v0);
+    r += potential_eval(t1, &v1);
+    r += potential_eval(t2, &v2);
+    r += potential_eval(t3, &v3);
+    return gradient_from(r, v0, v1, v2, v3, cd, px, py);
+}
+
 struct PathState {        // lets a long path continue across launches
     float x, y;
     float hx[5], hy[5];   // the previous points, most recent first
@@ -302,15 +467,26 @@ struct PathState {        // lets a long path continue across launches
     int status;           // -1 running, otherwise the final return code
 };
 
-// One thread per path.  Emits up to `chunk` further points into out[path * chunk * 2 ...] and
-// returns; the host relaunches while any path is still running.  `points` counts over all launches.
-__global__ void path_2d_kernel(FieldView2D f, uint32_t count, const float *__restrict__ starts, float step,
-                               float cd, uint64_t max_floats, uint32_t chunk, PathState *states,
-                               float *__restrict__ out, uint32_t *__restrict__ emitted, uint32_t first_launch)
+// One WARP per path (kPathWarps paths per CTA).  A streamline is sequential -- each point needs the gradient at
+// the previous one -- so the time per point is the length of the dependent chain: the warp shortens it by doing
+// the independent pieces of a step side by side.  Lane p < 4 fetches and blends the p-th potential of the central
+// difference (six independent loads, one memory round trip), lane 4 fetches the lock bit of the current cell,
+// lanes 0..4 each measure the distance to one of the five previous points (the reference's stuck test,
+// harmonic_path_cpu.cpp:121-151, one double sqrt each instead of five in a row); a vote and four shuffles bring
+// the results together and every lane then advances the same state with the reference's float operations in
+// the reference's order.  Emits up to `chunk` further points into out[path * chunk * 2 ...] and returns; the host
+// relaunches while any path is still running.  `points` counts over all launches.
+constexpr int kPathWarps = 4;
+
+__global__ void __launch_bounds__(32 * kPathWarps)
+path_2d_kernel(FieldView2D f, uint32_t count, const float *__restrict__ starts, float step, float cd,
+               uint64_t max_floats, uint32_t chunk, PathState *states, float *__restrict__ out,
+               uint32_t *__restrict__ emitted, uint32_t first_launch)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t i = blockIdx.x * kPathWarps + (threadIdx.x >> 5);
     if (i >= count) {
-        return;
+        return;     // warp-uniform
     }
     PathState s;
     float *o = out + (uint64_t)i * chunk * 2;
@@ -318,14 +494,25 @@ __global__ void path_2d_kernel(FieldView2D f, uint32_t count, const float *__res
     if (first_launch) {
         s.x = starts[2 * i];
         s.y = starts[2 * i + 1];
+        for (int h = 0; h < 5; ++h) {
+            s.hx[h] = s.hy[h] = 0.0f;
+        }
         s.nhist = 0;
         s.points = 0;
         s.status = -1;
-        if (cell_blocked(f, f2u_x86(__fadd_rn(s.x, 0.5f)), f2u_x86(__fadd_rn(s.y, 0.5f)))) {
+        const uint32_t xc = f2u_x86(__fadd_rn(s.x, 0.5f)), yc = f2u_x86(__fadd_rn(s.y, 0.5f));
+        bool blocked = xc >= f.m1 || yc >= f.m0;
+        if (!blocked) {
+            const bool locked = ((cell_mask_word(f, xc, yc) >> (xc & 31u)) & 1u) == 0u;
+            blocked = locked && cell_u(f, xc, yc) < 0.0f;
+        }
+        if (blocked) {
             s.status = kPathInvalidLocation;
         } else {
-            o[0] = s.x;
-            o[1] = s.y;
+            if (lane == 0) {
+                o[0] = s.x;
+                o[1] = s.y;
+            }
             n = 1;
             s.points = 1;
         }
@@ -334,14 +521,41 @@ __global__ void path_2d_kernel(FieldView2D f, uint32_t count, const float *__res
     }
     const float half_step = __fdiv_rn(step, 2.0f);
     while (s.status == -1 && n < chunk) {
-        // loop condition of harmonic_path_cpu.cpp:185-187, evaluated on the current point
-        const uint32_t xc = f2u_x86(__fadd_rn(s.x, 0.5f)), yc = f2u_x86(__fadd_rn(s.y, 0.5f));
-        bool stop = (xc >= f.m1 || yc >= f.m0) || cell_locked(f, xc, yc);
-        for (uint32_t h = 0; h < s.nhist && !stop; ++h) {
-            const double dx = (double)__fsub_rn(s.x, s.hx[h]), dy = (double)__fsub_rn(s.y, s.hy[h]);
-            const float dist = __double2float_rn(__dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy))));
-            stop = dist < half_step;
+        // ---- this lane's share of the step -------------------------------------------------------------
+        // lanes 0..3: potential at (x -/+ cd, y), (x, y -/+ cd); lane 4: lock bit of the current cell
+        const float qx = (lane == 0) ? __fsub_rn(s.x, cd) : ((lane == 1) ? __fadd_rn(s.x, cd) : s.x);
+        const float qy = (lane == 2) ? __fsub_rn(s.y, cd) : ((lane == 3) ? __fadd_rn(s.y, cd) : s.y);
+        PotentialTaps t;
+        float v = 0.0f;
+        int pr = kPathOk;
+        bool stop_here = false;
+        if (lane < 4u) {
+            potential_fetch(f, qx, qy, t);
+        } else if (lane == 4u) {
+            // loop condition of harmonic_path_cpu.cpp:185-187, evaluated on the current point
+            const uint32_t xc = f2u_x86(__fadd_rn(s.x, 0.5f)), yc = f2u_x86(__fadd_rn(s.y, 0.5f));
+            stop_here = (xc >= f.m1 || yc >= f.m0) || ((cell_mask_word(f, xc, yc) >> (xc & 31u)) & 1u) == 0u;
         }
+        // lanes 0..4: distance to the lane-th previous point (independent of the loads above)
+        bool near = false;
+        if (lane < s.nhist) {
+            float hxl = s.hx[0], hyl = s.hy[0];
+#pragma unroll
+            for (int h = 1; h < 5; ++h) {
+                if (lane == (uint32_t)h) {
+                    hxl = s.hx[h];
+                    hyl = s.hy[h];
+                }
+            }
+            const double dx = (double)__fsub_rn(s.x, hxl), dy = (double)__fsub_rn(s.y, hyl);
+            const float dist = __double2float_rn(__dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy))));
+            near = dist < half_step;
+        }
+        if (lane < 4u) {
+            pr = potential_eval(t, &v);
+        }
+        // ---- together ------------------------------------------------------------------------------------
+        bool stop = __any_sync(0xffffffffu, stop_here || near);
         if (!stop && (uint64_t)s.points * 2ull >= max_floats) {
             stop = true;
         }
@@ -349,11 +563,15 @@ __global__ void path_2d_kernel(FieldView2D f, uint32_t count, const float *__res
             s.status = (s.points <= 2u) ? kPathInvalidPath : kPathOk;
             break;
         }
+        const int bad = __any_sync(0xffffffffu, pr != kPathOk) ? 1 : 0;
+        const float v0 = __shfl_sync(0xffffffffu, v, 0), v1 = __shfl_sync(0xffffffffu, v, 1);
+        const float v2 = __shfl_sync(0xffffffffu, v, 2), v3 = __shfl_sync(0xffffffffu, v, 3);
         float gx, gy;
-        if (gradient_2d(f, s.x, s.y, cd, &gx, &gy) != kPathOk) {
+        if (gradient_from(bad, v0, v1, v2, v3, cd, &gx, &gy) != kPathOk) {
             s.status = kPathInvalidGradient;
             break;
         }
+#pragma unroll
         for (int h = 4; h > 0; --h) {
             s.hx[h] = s.hx[h - 1];
             s.hy[h] = s.hy[h - 1];
@@ -365,13 +583,17 @@ __global__ void path_2d_kernel(FieldView2D f, uint32_t count, const float *__res
         }
         s.x = __fadd_rn(s.x, __fmul_rn(gx, step));
         s.y = __fadd_rn(s.y, __fmul_rn(gy, step));
-        o[2 * n] = s.x;
-        o[2 * n + 1] = s.y;
+        if (lane == 0) {
+            o[2 * n] = s.x;
+            o[2 * n + 1] = s.y;
+        }
         n++;
         s.points++;
     }
-    states[i] = s;
-    emitted[i] = n;
+    if (lane == 0) {
+        states[i] = s;
+        emitted[i] = n;
+    }
 }
 
 __global__ void potential_gradient_kernel(FieldView2D f, float x, float y, float cd, int want_gradient,

@@ -17,19 +17,18 @@
 
 namespace epic_b200 {
 
-// Shared-memory image of the libm tables, split into 32-bit words so that a warp's 32 random
-// lookups hit 32 distinct banks (or broadcast): conflict-free LDS.32.
-struct MathTables {
+// Shared-memory image of the logf tables, one 16-byte entry per (exponent, interval): a single LDS.128 per
+// logarithm.  The 32-entry expf table does not live in shared memory at all: lane i of every warp keeps entry i in
+// two registers and a lookup is a pair of SHFL.IDX (the index needs no masking and no address arithmetic: the
+// shuffle takes the source lane modulo 32).  Both replace the ten LDS.32 + index arithmetic of the round-1 layout
+// (32-bit words for bank freedom): the strict sweep is bound by instruction issue, not by shared-memory bandwidth.
+struct alignas(16) MathTables {
+    // {invc[i] * 2^-k (exact), fma(k, Ln2, logc[i])} at index k*16 + i, k = 0..3: the log argument is a sum of
+    // 2n <= 6 terms in [1, 6], for which glibc's exponent k is 0..3, so its first FMA (and the int -> double
+    // conversion of k) becomes a lookup of the identical double; see strict_logf_sum in strict_math.h.
+    double2 logt[64];
     uint32_t exp_hi[32];
     uint32_t exp_lo[32];
-    // invc[k*16 + i] = invc[i] * 2^-k (exact), see strict_logf_sum in strict_math.h
-    uint32_t invc_hi[64];
-    uint32_t invc_lo[64];
-    // y0[k*16 + i] = fma(k, Ln2, logc[i]) for k = 0..3: the log argument is a sum of 2n <= 6 terms in
-    // [1, 6], for which glibc's exponent k is 0..3, so its first FMA (and the int -> double conversion
-    // of k) becomes a lookup of the identical double.
-    uint32_t y0_hi[64];
-    uint32_t y0_lo[64];
 };
 
 static __device__ __constant__ uint64_t c_exp2f_table[32] = {EPIC_EXP2F_TABLE};
@@ -43,12 +42,10 @@ __device__ __forceinline__ void load_math_tables(MathTables *t, int tid, int nth
     }
     for (int i = tid; i < 64; i += nthreads) {
         const uint64_t a = (uint64_t)__double_as_longlong(c_logf_table[2 * (i & 15)]) - ((uint64_t)(i >> 4) << 52);
-        t->invc_hi[i] = (uint32_t)(a >> 32);
-        t->invc_lo[i] = (uint32_t)a;
-        const double y0 = __fma_rn((double)(i >> 4), kLogLn2, c_logf_table[2 * (i & 15) + 1]);
-        const uint64_t b = (uint64_t)__double_as_longlong(y0);
-        t->y0_hi[i] = (uint32_t)(b >> 32);
-        t->y0_lo[i] = (uint32_t)b;
+        double2 e;
+        e.x = __longlong_as_double((long long)a);
+        e.y = __fma_rn((double)(i >> 4), kLogLn2, c_logf_table[2 * (i & 15) + 1]);
+        t->logt[i] = e;
     }
 }
 
@@ -64,6 +61,7 @@ struct alignas(16) StrictMath {
     double c0, c1, c2; // kExpC0..2
     double ln2, a0, a1, a2;
     const MathTables *t;
+    uint32_t thi, tlo;  // this lane's entry of the expf table (lane i holds T[i])
     static constexpr bool kUsesTables = true;
 
     __host__ __device__ void init(double log_2n)
@@ -81,9 +79,16 @@ struct alignas(16) StrictMath {
         a2 = kLogA2;
     }
 
-    __device__ __forceinline__ void bind(const MathTables *tables) { t = tables; }
+    // After load_math_tables() and a barrier.
+    __device__ __forceinline__ void bind(const MathTables *tables)
+    {
+        t = tables;
+        thi = tables->exp_hi[threadIdx.x & 31];
+        tlo = tables->exp_lo[threadIdx.x & 31];
+    }
 
-    // strict_expf_nonpos (strict_math.h), table split into 32-bit words.
+    // strict_expf_nonpos (strict_math.h).  WARP-SYNCHRONOUS: all 32 lanes must call it together (the table
+    // lookup is a shuffle); the sweeps call it after a warp vote, with every lane computing.
     __device__ __forceinline__ float exp_nonpos(float x) const
     {
         // widening on the bit pattern (strict_widen_nonpos): two integer operations on lightly loaded
@@ -94,8 +99,9 @@ struct alignas(16) StrictMath {
         const uint32_t ki = (uint32_t)__double2loint(kdp);
         const double kd = __dadd_rn(kdp, -shift);
         const double r = __fma_rn(inv_ln2n, xd, -kd);
-        const uint32_t idx = ki & 31u;
-        const double s = __hiloint2double((int)(t->exp_hi[idx] + (ki << 15)), (int)t->exp_lo[idx]);
+        const uint32_t shi = __shfl_sync(0xffffffffu, thi, (int)ki);   // source lane = ki mod 32
+        const uint32_t slo = __shfl_sync(0xffffffffu, tlo, (int)ki);
+        const double s = __hiloint2double((int)(shi + (ki << 15)), (int)slo);
         double y = __fma_rn(c0, r, c1);
         y = __fma_rn(y, r, c2);
         const double sr = __dmul_rn(s, r);
@@ -106,9 +112,11 @@ struct alignas(16) StrictMath {
     __device__ __forceinline__ float log_sum(float x) const
     {
         const uint32_t ix = __float_as_uint(x);
-        const uint32_t ki = ((ix - 0x3f330000u) >> 19) & 63u;   // k * 16 + i, k <= 3
-        const double invc = __hiloint2double((int)t->invc_hi[ki], (int)t->invc_lo[ki]);
-        const double y0 = __hiloint2double((int)t->y0_hi[ki], (int)t->y0_lo[ki]);
+        // byte offset of entry k * 16 + i (k <= 3): ((ix - 0x3f330000) >> 19 & 63) * 16; the constant has no bits
+        // below 2^15, so the subtraction commutes with the shift and the pair becomes one LEA.HI
+        const uint32_t off = ((ix >> 15) - (0x3f330000u >> 15)) & 0x3f0u;
+        const double2 e = *reinterpret_cast<const double2 *>(reinterpret_cast<const char *>(t->logt) + off);
+        const double invc = e.x, y0 = e.y;
         const double xd = __hiloint2double((int)((ix >> 3) + 0x38000000u), (int)(ix << 29));
         const double r = __fma_rn(xd, invc, -1.0);
         double y = __fma_rn(a0, r, a1);

@@ -286,7 +286,15 @@ sweep2d_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constan
     constexpr bool TRACK = (MODE & kTrack) != 0;
     constexpr bool P2P = (MODE & kP2P) != 0;
     if (*p.ctrl_done) {
-        return;  // a previous check sweep already met the termination rule
+        // A previous check sweep already met the termination rule: the pass retires as a no-op.  The neighbouring
+        // slabs retire the same pass the same way (the decision is global), but the host has counted it, so the
+        // pass index still has to reach the neighbours' flag words or the first pass after the solve would wait
+        // for it forever.
+        if (P2P && p.p2p_sync != 0 && blockIdx.x == 0 && threadIdx.x == 0) {
+            if (p.signal_up != nullptr) st_release_sys(p.signal_up, p.pass_index);
+            if (p.signal_dn != nullptr) st_release_sys(p.signal_dn, p.pass_index);
+        }
+        return;
     }
     const bool p2p = P2P && p.p2p_sync != 0;    // edge tile rows first only when they synchronise in the kernel
     const int tx = blockIdx.x % p.ntx, ty = tile_row_of(blockIdx.x / p.ntx, (int)p.nty, p2p);

@@ -86,7 +86,8 @@ def procedural_maze(shape, corridor=8, wall=2, goals=4, seed=1234, row0=0, rows=
     """BASELINE.json config 4: a perfect maze (binary-tree construction: every coarse cell opens
     a passage either towards -row or towards +column, chosen by a per-coarse-row seeded coin) with
     corridors `corridor` cells wide and walls `wall` cells thick.  The construction is local, so
-    any slab of rows can be generated on its own."""
+    any slab of rows can be generated on its own (one numpy row pattern per coarse row: a 65536-wide
+    slab of 8192 rows takes seconds)."""
     shape = tuple(int(s) for s in shape)
     assert len(shape) == 2
     rows = shape[0] - row0 if rows is None else rows
@@ -95,6 +96,10 @@ def procedural_maze(shape, corridor=8, wall=2, goals=4, seed=1234, row0=0, rows=
     obst = np.ones((rows, shape[1]), dtype=bool)
     cy_lo = max(0, (row0 - wall) // pitch - 1)
     cy_hi = min(ncy, (row0 + rows) // pitch + 2)
+    col = np.arange(shape[1])
+    cell_of = np.clip((col - wall) // pitch, 0, max(ncx - 1, 0))
+    in_cell = (col >= wall) & (col < wall + ncx * pitch)
+    off = col - (wall + cell_of * pitch)              # offset inside the coarse cell: [0, pitch)
     for cy in range(cy_lo, cy_hi):
         rng = np.random.RandomState([seed & 0x7FFFFFFF, cy])
         coin = rng.random_sample(ncx) < 0.5          # True: open towards +column
@@ -103,16 +108,17 @@ def procedural_maze(shape, corridor=8, wall=2, goals=4, seed=1234, row0=0, rows=
             coin[:] = True                            # first row must open towards +column
             coin[ncx - 1] = False
         y0 = wall + cy * pitch                        # first corridor row of this coarse row
-        for cx in range(ncx):
-            x0 = wall + cx * pitch
-            ya, yb, xa, xb = y0, y0 + corridor, x0, x0 + corridor
-            if coin[cx]:
-                xb += wall                            # carve through the wall on the +column side
-            elif cy > 0:
-                ya -= wall                            # carve through the wall on the -row side
-            ya, yb = max(ya, row0), min(yb, row0 + rows)
+        # corridor rows: the corridor itself, plus the wall on the +column side where the coin says so
+        open_corr = in_cell & ((off < corridor) | coin[cell_of])
+        ya, yb = max(y0, row0), min(y0 + corridor, row0 + rows)
+        if ya < yb:
+            obst[ya - row0:yb - row0, open_corr] = False
+        if cy > 0:
+            # the wall rows above: carved through (corridor columns only) where the cell opens towards -row
+            open_wall = in_cell & (off < corridor) & ~coin[cell_of]
+            ya, yb = max(y0 - wall, row0), min(y0, row0 + rows)
             if ya < yb:
-                obst[ya - row0:yb - row0, xa:xb] = False
+                obst[ya - row0:yb - row0, open_wall] = False
     rng = np.random.RandomState(seed ^ 0x5EED)
     gc = np.stack([wall + rng.randint(0, ncy, size=goals) * pitch + corridor // 2,
                    wall + rng.randint(0, ncx, size=goals) * pitch + corridor // 2], axis=1)

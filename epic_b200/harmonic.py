@@ -79,6 +79,17 @@ class Harmonic(le.EpicHarmonic):
         self._call("harmonic_get_potential_values_gpu")
         return self._u
 
+    def gpu_stats(self):
+        """Extension: how the library holds this grid on the device(s) and what its last solve did (slabs,
+        launches, device seconds / iterations / delta of the last harmonic_execute_gpu, tiles skipped per slab)."""
+        st = le.GridStats()
+        r = le.load().epic_b200_harmonic_stats(ct.cast(ct.byref(self), ct.c_void_p), ct.byref(st))
+        if r != le.EPIC_SUCCESS:
+            raise EpicError("epic_b200_harmonic_stats", r)
+        return {"slabs": st.slabs, "launches": st.launches, "last_solve_seconds": st.last_solve_seconds,
+                "last_solve_iterations": st.last_solve_iterations, "last_solve_delta": st.last_solve_delta,
+                "skipped_tiles": [int(st.skipped_tiles[i]) for i in range(st.slabs)]}
+
     # -- solving -------------------------------------------------------------------------------------
     def solve(self, algorithm='gauss-seidel', process='gpu', numThreads=1024, epsilon=None):
         """Reference signature (harmonic.py:56).  Returns (wall seconds, cpu seconds) of the solver call."""

@@ -50,6 +50,13 @@ class FieldInfo(ct.Structure):
                 ("math", ct.c_uint32), ("device", ct.c_int32), ("skipped_tiles", ct.c_uint64)]
 
 
+class GridStats(ct.Structure):
+    """epic_b200_stats (include/epic_b200.h)."""
+    _fields_ = [("slabs", ct.c_uint32), ("last_solve_iterations", ct.c_uint32), ("last_solve_delta", ct.c_float),
+                ("reserved", ct.c_uint32), ("last_solve_seconds", ct.c_double), ("launches", ct.c_uint64),
+                ("skipped_tiles", ct.c_uint64 * 16)]
+
+
 def build(force=False):
     """Compile libepic.so in-tree (nvcc, sm_100a)."""
     if force:
@@ -140,6 +147,7 @@ EXTENSION_EXPORTS = {
     "epic_b200_field_peer_export": (_F, ct.c_void_p, ct.c_uint64),
     "epic_b200_field_set_peer_ipc": (_F, ct.c_int, ct.c_void_p, ct.c_uint64),
     "epic_b200_field_set_peer_local": (_F, ct.c_int, _F),
+    "epic_b200_harmonic_stats": (ct.c_void_p, _P(GridStats)),
     "epic_b200_selftest_math": (ct.c_uint32, _P(ct.c_uint64), _P(ct.c_uint64), _P(ct.c_uint64), _P(ct.c_uint64)),
     "epic_b200_field_paths_2d": (_F, ct.c_uint32, _P(ct.c_float), ct.c_float, ct.c_float, ct.c_uint32, _P(ct.c_int),
                                  _P(ct.c_uint32), _P(_P(ct.c_float))),

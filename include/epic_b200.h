@@ -94,6 +94,21 @@ int epic_b200_field_paths_2d(epic_b200_field *f, uint32_t count, const float *st
                              uint32_t max_length, int *results, uint32_t *k, float **paths);
 void epic_b200_free_path(float *path);
 
+/* What the grid behind a libepic `Harmonic` struct (its d_* handles) looks like and did last: how many slabs the
+ * library sharded it into (EPIC_DEVICES), kernels launched, the duration / iteration count / delta of the most recent
+ * harmonic_execute_gpu solve (device time of the loop, without the copies around it), and how many tile passes each
+ * slab skipped as static -- the load balance of a sharded solve.  `harmonic` is a `const epic::Harmonic *`. */
+typedef struct epic_b200_stats {
+    uint32_t slabs;
+    uint32_t last_solve_iterations;
+    float last_solve_delta;
+    uint32_t reserved;
+    double last_solve_seconds;
+    uint64_t launches;
+    uint64_t skipped_tiles[16];
+} epic_b200_stats;
+int epic_b200_harmonic_stats(const void *harmonic, epic_b200_stats *out);
+
 /* Self-test: the strict-math device functions (bit-exact twins of glibc expf / logf, see
  * epic_b200/csrc/kernels/strict_math.h) against THIS host's libm, over every `stride`-th float of the
  * argument ranges the sweep can produce (x <= 0 for expf, [1, 8] for logf). */

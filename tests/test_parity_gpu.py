@@ -120,6 +120,29 @@ def test_execute_gpu_error_codes(libepic_built):
     h.uninitialize_gpu()
 
 
+@pytest.mark.parametrize("k", [1, 2, 3, 5])
+def test_update_gpu_then_execute_gpu_keeps_the_queued_sweeps(libepic_built, k):
+    """harmonic_update_gpu x k (k not a multiple of the pass depth T = 4, so sweeps are still queued inside the
+    library) followed by harmonic_execute_gpu: the reference has applied those sweeps to d_u before execute
+    resets currentIteration (harmonic_gpu.cu:226-262), so the solve must start from the swept field."""
+    u, locked, eps, stagger = common.case_input("random_ragged")
+    h = Harmonic(u.copy(), locked.copy(), eps, stagger)
+    h.initialize_gpu()
+    L = libepic_built
+    for _ in range(k):
+        assert L.harmonic_update_gpu(ct.byref(h), 1024) == 0
+    assert h.currentIteration == k
+    o = orc.Oracle(u.copy(), locked.copy(), eps, stagger)
+    o.run_iterations(k)          # iterations 0 .. k-1: the same cells, whether or not delta is taken
+    o.iteration = 0
+    assert o.complete() == 0
+    assert L.harmonic_execute_gpu(ct.byref(h), 1024) == 0
+    assert h.currentIteration == o.iteration
+    assert h.delta == o.delta
+    assert np.array_equal(h.field, o.u)
+    h.uninitialize_gpu()
+
+
 def test_update_model_reuploads(libepic_built):
     u, locked, eps, stagger = common.case_input("random_ragged")
     s = common.LibepicSolver(u.copy(), locked.copy(), eps, stagger, "gpu")
