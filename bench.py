@@ -285,9 +285,15 @@ def reference_gpu_baseline(args):
             return json.loads(lines[-1]) if lines else {"error": (r.stderr or "no output")[-300:]}
         except subprocess.TimeoutExpired:
             return {"error": "timed out after %d s" % timeout}
-    if args.dims == 2 and args.size <= 16384:
-        out["sweeps"] = sub(["sweeps", "--size", str(args.size), "--steps", "10", "--warmup", "2"], 300)
-    out["maze"] = sub(["complete", "--map", "maze"], 180)
+    # The stock build: its sweep kernels call __syncthreads() in divergent code (reference harmonic_gpu.cu:46-49,
+    # :86-89), which deadlocks on Volta and later (SASS: WARPSYNC.ALL on both sides of the divergent branch;
+    # profiles/r02_reference_gpu.md).  One short attempt records that on this box; the numbers come from the build
+    # with the barriers compiled out (oracle/Makefile refgpu_nobar), through harmonic_update_gpu, which needs none.
+    out["stock_complete_gpu_maze"] = sub(["complete", "--map", "maze"], 25)
+    if ref_gpu.available("nobar"):
+        if args.dims == 2 and args.size <= 16384:
+            out["sweeps"] = sub(["sweeps", "--variant", "nobar", "--size", str(args.size), "--steps", "10", "--warmup", "2"], 300)
+        out["maze"] = sub(["updates", "--variant", "nobar", "--map", "maze", "--iterations", "49301"], 180)
     # ours, same call, same map
     try:
         from epic_b200 import grids

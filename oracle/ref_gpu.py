@@ -27,15 +27,19 @@ ROOT = os.path.dirname(HERE)
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 REF_GPU_SO = os.path.join(HERE, "_ref", "libepic_ref_gpu.so")
+# the same sources with __syncthreads() compiled out (oracle/Makefile, target refgpu_nobar): the stock build's
+# divergent barriers deadlock on Volta and later, see profiles/r02_reference_gpu.md
+REF_GPU_NOBAR_SO = os.path.join(HERE, "_ref", "libepic_ref_gpu_nobar.so")
+_variant = "stock"
 
 
-def available():
-    return os.path.exists(REF_GPU_SO)
+def available(variant="stock"):
+    return os.path.exists(REF_GPU_SO if variant == "stock" else REF_GPU_NOBAR_SO)
 
 
 def _lib():
     from oracle.oracle import RefHarmonic
-    R = ct.CDLL(REF_GPU_SO)
+    R = ct.CDLL(REF_GPU_SO if _variant == "stock" else REF_GPU_NOBAR_SO)
     P = ct.POINTER(RefHarmonic)
     for name in ("harmonic_initialize_dimension_size_gpu", "harmonic_initialize_potential_values_gpu",
                  "harmonic_initialize_locked_gpu", "harmonic_uninitialize_dimension_size_gpu",
@@ -74,7 +78,8 @@ def sweeps(size, steps, warmup, threads=1024):
     r += R.harmonic_initialize_gpu(ct.byref(h), threads)
     if r != 0:
         return {"error": "initialize returned %d" % r}
-    R.harmonic_update_and_check_gpu(ct.byref(h), threads)
+    if _variant == "stock":
+        R.harmonic_update_and_check_gpu(ct.byref(h), threads)
     for _ in range(warmup):
         R.harmonic_update_gpu(ct.byref(h), threads)
     t0 = time.perf_counter()
@@ -82,14 +87,15 @@ def sweeps(size, steps, warmup, threads=1024):
         r += R.harmonic_update_gpu(ct.byref(h), threads)
     dt = time.perf_counter() - t0
     t1 = time.perf_counter()
-    rc = R.harmonic_update_and_check_gpu(ct.byref(h), threads)
+    rc = R.harmonic_update_and_check_gpu(ct.byref(h), threads) if _variant == "stock" else -1
     dt_check = time.perf_counter() - t1
     R.harmonic_uninitialize_gpu(ct.byref(h))
     R.harmonic_uninitialize_dimension_size_gpu(ct.byref(h))
     R.harmonic_uninitialize_potential_values_gpu(ct.byref(h))
     R.harmonic_uninitialize_locked_gpu(ct.byref(h))
     updates = float(size) * size / 2.0 * steps
-    return {"kind": "reference GPU kernels (harmonic_gpu.cu) recompiled for sm_100a, stock host loop",
+    return {"kind": "reference GPU kernels (harmonic_gpu.cu) recompiled for sm_100a, stock host loop" +
+                    ("" if _variant == "stock" else "; __syncthreads() compiled out (the stock build deadlocks)"),
             "what": "%d x harmonic_update_gpu (1 half-sweep + cudaDeviceSynchronize each), %dx%d random-obstacle grid, "
                     "numThreads %d" % (steps, size, size, threads),
             "value": updates / dt / 1e9, "unit": "Gcell-updates/s", "ms_per_half_sweep": dt / steps * 1e3,
@@ -116,19 +122,64 @@ def complete(name, threads=1024):
             "gcups": float(u.size) / 2.0 * h.currentIteration / dt / 1e9}
 
 
+def updates(name, iterations, threads=1024):
+    """Wall time of `iterations` harmonic_update_gpu calls on a demo map, device-resident (H2D before, D2H after,
+    both timed separately): what the reference's host loop + kernel cost for that many half-sweeps.  No
+    convergence checks (the nobar build's check kernel is unusable), so this is a LOWER bound of a solve."""
+    from epic_b200 import grids
+    maps = np.load(os.path.join(ROOT, "tests", "golden", "maps.npz"))
+    u, locked = grids.grid_from_image(maps[name])
+    R = _lib()
+    h, _m = _harmonic(u, locked, 1e-3, 100)
+    t0 = time.perf_counter()
+    r = R.harmonic_initialize_dimension_size_gpu(ct.byref(h))
+    r += R.harmonic_initialize_potential_values_gpu(ct.byref(h))
+    r += R.harmonic_initialize_locked_gpu(ct.byref(h))
+    t_up = time.perf_counter() - t0
+    if r != 0:
+        return {"error": "initialize returned %d" % r}
+    for _ in range(200):
+        R.harmonic_update_gpu(ct.byref(h), threads)
+    t0 = time.perf_counter()
+    for _ in range(iterations):
+        r += R.harmonic_update_gpu(ct.byref(h), threads)
+    dt = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    R.harmonic_get_potential_values_gpu(ct.byref(h))
+    t_down = time.perf_counter() - t0
+    R.harmonic_uninitialize_dimension_size_gpu(ct.byref(h))
+    R.harmonic_uninitialize_potential_values_gpu(ct.byref(h))
+    R.harmonic_uninitialize_locked_gpu(ct.byref(h))
+    return {"kind": "reference GPU kernels recompiled for sm_100a" +
+                    ("" if _variant == "stock" else "; __syncthreads() compiled out (the stock build deadlocks)"),
+            "what": "%d x harmonic_update_gpu on maps '%s' %s (the iteration count of the reference CPU solve at eps 1e-3); "
+                    "no convergence checks" % (iterations, name, "x".join(str(s) for s in u.shape)),
+            "seconds": dt, "us_per_half_sweep": dt / iterations * 1e6, "upload_seconds": t_up, "download_seconds": t_down,
+            "errors": int(r), "gcups": float(u.size) / 2.0 * iterations / dt / 1e9}
+
+
 def main():
+    global _variant
     ap = argparse.ArgumentParser()
-    ap.add_argument("mode", choices=["sweeps", "complete"])
+    ap.add_argument("mode", choices=["sweeps", "complete", "updates"])
+    ap.add_argument("--variant", choices=["stock", "nobar"], default="stock")
+    ap.add_argument("--iterations", type=int, default=49301)
     ap.add_argument("--size", type=int, default=16384)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--map", default="maze")
     ap.add_argument("--threads", type=int, default=1024)
     a = ap.parse_args()
-    if not available():
-        print(json.dumps({"unavailable": "oracle/_ref/libepic_ref_gpu.so was not built (no /root/reference at build time)"}))
+    _variant = a.variant
+    if not available(a.variant):
+        print(json.dumps({"unavailable": "oracle/_ref/libepic_ref_gpu*.so was not built (no /root/reference at build time)"}))
         return
-    out = sweeps(a.size, a.steps, a.warmup, a.threads) if a.mode == "sweeps" else complete(a.map, a.threads)
+    if a.mode == "sweeps":
+        out = sweeps(a.size, a.steps, a.warmup, a.threads)
+    elif a.mode == "complete":
+        out = complete(a.map, a.threads)
+    else:
+        out = updates(a.map, a.iterations, a.threads)
     print(json.dumps(out), flush=True)
 
 

@@ -93,7 +93,30 @@ def case_map(name, images, starts, full=True):
         n = u.size
         rec["paths"] = [path_record(ref, x, y, 0.05, 0.5, int(n / 0.05)) for x, y in starts]
         rec["paths"] += [path_record(ref, x, y, 0.2, 0.4, 1000000) for x, y in starts]
+        rec["potentials"] = potential_records(ref, locked, seed=len(name))
     return rec
+
+
+def potential_records(ref, locked, seed, count=40):
+    """Bilinear potentials and central-difference gradients (harmonic_path_cpu.cpp:41-118) at seeded sub-cell
+    positions: free cells with fractional offsets (some next to obstacles, where a tap or the gradient fails),
+    plus positions on obstacles and at the border."""
+    rng = np.random.RandomState(1000 + seed)
+    pts = []
+    for x, y in grids.free_cells(locked, count, seed=seed + 3):
+        pts.append((np.float32(x + rng.uniform(-0.49, 0.49)), np.float32(y + rng.uniform(-0.49, 0.49))))
+    ys, xs = np.nonzero(locked == 1)
+    for i in rng.choice(len(ys), 6, replace=False):
+        pts.append((np.float32(xs[i] + 0.25), np.float32(ys[i] - 0.25)))
+    pts += [(np.float32(0.2), np.float32(locked.shape[0] / 2)), (np.float32(locked.shape[1] - 0.6), np.float32(1.5))]
+    out = []
+    for x, y in pts:
+        x, y = float(x), float(y)
+        r, v = ref.potential(x, y)
+        rg, gx, gy = ref.gradient(x, y, 0.5)
+        out.append({"xy": [x, y], "ret": int(r), "value_hex": float(v).hex(), "grad_ret": int(rg),
+                    "grad_hex": [float(gx).hex(), float(gy).hex()]})
+    return out
 
 
 def case_box64():

@@ -15,7 +15,8 @@ import replay  # noqa: E402
 with tempfile.TemporaryDirectory() as tmp:
     exe = replay.build(os.path.join(tmp, "replay_ref"), include=replay.REF_INC, libdir=replay.REF_LIBDIR,
                        lib="epic_ref_cpu", cpu_only=True)
-    gold = {"plan": replay.run(exe, replay.plan_case(tmp), "cpu"), "node": replay.run(exe, replay.node_case(tmp), "cpu")}
+    gold = {"plan": replay.run(exe, replay.plan_case(tmp), "cpu"), "node": replay.run(exe, replay.node_case(tmp), "cpu"),
+            "plan_umass": replay.run(exe, replay.plan_umass_case(tmp), "cpu", timeout=1200)}
 with open(replay.GOLDEN, "w") as f:
     json.dump(gold, f, indent=1, sort_keys=True)
 print(json.dumps(gold, indent=1, sort_keys=True))

@@ -61,6 +61,18 @@ def plan_case(tmp):
     return ["plan", path, None, str(int(gx)), str(int(gy)), "%.4f" % (OX + (sx + 0.25) * RES), "%.4f" % (OY + (sy + 0.25) * RES)]
 
 
+def plan_umass_case(tmp):
+    """BASELINE.json config 2(ii): the plugin on maps/umass.png as map_server + costmap_2d hand it over -- black
+    pixels are lethal (254), everything else (150 = unknown, 255 = free) is free space (cost 0), the plugin itself
+    locks the border (reference src/epic_nav_core_plugin.cpp:109-187); goal = the map's goal cell (column 779,
+    row 9), start = the first of the golden streamline starts (339, 184)."""
+    image = common.maps()["umass"]
+    cost = np.where(image == 0, 254, 0).astype(np.uint8)
+    path = os.path.join(tmp, "plan_umass_map.bin")
+    write_map(path, cost)
+    return ["plan", path, None, "779", "9", "%.4f" % (OX + (339 + 0.25) * RES), "%.4f" % (OY + (184 + 0.25) * RES)]
+
+
 def node_case(tmp):
     """The node on a procedural maze delivered as an OccupancyGrid: 100 = wall, 0 = free, a band of -1
     (unknown, treated as free) and a band of -2 (no change: those cells keep the node's initial state)."""
@@ -75,9 +87,9 @@ def node_case(tmp):
             "%.4f" % (OX + (sx + 0.3) * RES), "%.4f" % (OY + (sy + 0.6) * RES), "60", "50"]
 
 
-def run(exe, case, process):
+def run(exe, case, process, timeout=300):
     args = [exe] + [process if a is None else a for a in case]
-    r = subprocess.run(args, capture_output=True, text=True, timeout=300)
+    r = subprocess.run(args, capture_output=True, text=True, timeout=timeout)
     assert r.returncode == 0, (r.returncode, r.stdout[-2000:], r.stderr[-2000:])
     out = {}
     for line in r.stdout.splitlines():

@@ -85,6 +85,19 @@ def test_callers_on_the_gpu_match_the_reference(ours, gold, tmp_path, scenario, 
         check(out, gold["node"], extra=[("gpu_initialised", "1"), ("gpu_uninitialised", "1")])
 
 
+@pytest.mark.gpu
+def test_plugin_replay_on_umass_matches_the_reference(ours, gold, tmp_path):
+    """BASELINE.json config 2(ii): makePlan on maps/umass.png with the plugin's own costmap -> grid conversion;
+    the golden lines come from the same harness linked with the untouched reference CPU sources."""
+    out = replay.run(ours, replay.plan_umass_case(str(tmp_path)), "gpu")
+    check(out, gold["plan_umass"], extra=[("complete_gpu_result", "0")])
+
+
+@pytest.mark.skipif(not os.environ.get("EPIC_SLOW_TESTS"), reason="two minutes of CPU relaxation: set EPIC_SLOW_TESTS=1")
+def test_plugin_replay_on_umass_on_the_cpu_exports(ours, gold, tmp_path):
+    check(replay.run(ours, replay.plan_umass_case(str(tmp_path)), "cpu", timeout=1200), gold["plan_umass"])
+
+
 def _fnv(data, h=1469598103934665603):
     for b in data:
         h = ((h ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
