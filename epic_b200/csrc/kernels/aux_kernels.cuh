@@ -520,40 +520,37 @@ path_2d_kernel(FieldView2D f, uint32_t count, const float *__restrict__ starts, 
         s = states[i];
     }
     const float half_step = __fdiv_rn(step, 2.0f);
+    const uint32_t which = lane & 3u;      // this lane's potential of the central difference
     while (s.status == -1 && n < chunk) {
         // ---- this lane's share of the step -------------------------------------------------------------
-        // lanes 0..3: potential at (x -/+ cd, y), (x, y -/+ cd); lane 4: lock bit of the current cell
-        const float qx = (lane == 0) ? __fsub_rn(s.x, cd) : ((lane == 1) ? __fadd_rn(s.x, cd) : s.x);
-        const float qy = (lane == 2) ? __fsub_rn(s.y, cd) : ((lane == 3) ? __fadd_rn(s.y, cd) : s.y);
+        // EVERY lane runs the same instructions (no lane-dependent branch, which would serialise the pieces):
+        // the potential at (x -/+ cd, y) or (x, y -/+ cd) chosen by lane & 3, the lock bit of the current cell,
+        // and the distance to one of the previous points.  The three chains are independent of each other, so
+        // their latencies overlap inside the one instruction stream.
+        const float qx = (which == 0u) ? __fsub_rn(s.x, cd) : ((which == 1u) ? __fadd_rn(s.x, cd) : s.x);
+        const float qy = (which == 2u) ? __fsub_rn(s.y, cd) : ((which == 3u) ? __fadd_rn(s.y, cd) : s.y);
         PotentialTaps t;
-        float v = 0.0f;
-        int pr = kPathOk;
-        bool stop_here = false;
-        if (lane < 4u) {
-            potential_fetch(f, qx, qy, t);
-        } else if (lane == 4u) {
-            // loop condition of harmonic_path_cpu.cpp:185-187, evaluated on the current point
-            const uint32_t xc = f2u_x86(__fadd_rn(s.x, 0.5f)), yc = f2u_x86(__fadd_rn(s.y, 0.5f));
-            stop_here = (xc >= f.m1 || yc >= f.m0) || ((cell_mask_word(f, xc, yc) >> (xc & 31u)) & 1u) == 0u;
-        }
-        // lanes 0..4: distance to the lane-th previous point (independent of the loads above)
-        bool near = false;
-        if (lane < s.nhist) {
-            float hxl = s.hx[0], hyl = s.hy[0];
+        potential_fetch(f, qx, qy, t);
+        // loop condition of harmonic_path_cpu.cpp:185-187, evaluated on the current point
+        const uint32_t xc = f2u_x86(__fadd_rn(s.x, 0.5f)), yc = f2u_x86(__fadd_rn(s.y, 0.5f));
+        const bool outside = xc >= f.m1 || yc >= f.m0;
+        const uint32_t cword = outside ? 0u : cell_mask_word(f, xc, yc);
+        const bool stop_here = outside || ((cword >> (xc & 31u)) & 1u) == 0u;
+        // distance to the (lane mod 8)-th previous point (lanes whose index is not a valid history entry are ignored)
+        const uint32_t hidx = lane & 7u;
+        float hxl = s.hx[0], hyl = s.hy[0];
 #pragma unroll
-            for (int h = 1; h < 5; ++h) {
-                if (lane == (uint32_t)h) {
-                    hxl = s.hx[h];
-                    hyl = s.hy[h];
-                }
+        for (int h = 1; h < 5; ++h) {
+            if (hidx == (uint32_t)h) {
+                hxl = s.hx[h];
+                hyl = s.hy[h];
             }
-            const double dx = (double)__fsub_rn(s.x, hxl), dy = (double)__fsub_rn(s.y, hyl);
-            const float dist = __double2float_rn(__dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy))));
-            near = dist < half_step;
         }
-        if (lane < 4u) {
-            pr = potential_eval(t, &v);
-        }
+        const double ddx = (double)__fsub_rn(s.x, hxl), ddy = (double)__fsub_rn(s.y, hyl);
+        const float dist = __double2float_rn(__dsqrt_rn(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy))));
+        const bool near = hidx < s.nhist && dist < half_step;
+        float v = 0.0f;
+        const int pr = potential_eval(t, &v);
         // ---- together ------------------------------------------------------------------------------------
         bool stop = __any_sync(0xffffffffu, stop_here || near);
         if (!stop && (uint64_t)s.points * 2ull >= max_floats) {

@@ -279,7 +279,7 @@ struct RowCtx {
 enum { kPlain = 0, kTrack = 1, kP2P = 2 };
 
 template <class Math, int NT, int MODE = kPlain>
-__global__ void __launch_bounds__(NT, (NT <= 512 ? 2 : 1))
+__global__ void __launch_bounds__(NT, (NT <= 256 ? 3 : 2))
 sweep2d_kernel(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ Sweep2DParams p,
                const __grid_constant__ Math math_in)
 {

@@ -3,7 +3,9 @@
 Bit-exactness is the bar in the default (strict) math mode: fields, deltas and iteration counts are
 compared with golden vectors produced by the untouched reference CPU code (tests/golden/golden.json)
 and with the oracle on seeded inputs; paths are compared point for point.  The fast mode (MUFU
-ex2/lg2) is held to the stated tolerance |du| <= 1e-5*|u| + 1e-5 at equal iteration count.
+ex2/lg2) is a TOLERANCE mode: same iteration count at matched epsilon, |du| <= 1e-5*|u| + 4e-7*iterations
+(test_fast_mode_within_stated_tolerance_at_matched_epsilon explains the second term), streamlines within
+0.05 cell of the reference's but not cell-for-cell.
 """
 import ctypes as ct
 import os

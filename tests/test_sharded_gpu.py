@@ -121,6 +121,23 @@ def test_nccl_two_ranks_bit_identical(golden, libepic_built, tmp_path):
         assert res["sha1_u"] == g["sha1_u"], "%s over %s differs from the reference" % (case, halo)
 
 
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_maximum_size_2d_sharded_bands_against_oracle(libepic_built, tmp_path):
+    """BASELINE.json config 4's size (65536^2 = 2^32 cells, 33 GiB resident) row-sharded over every GPU of the box:
+    see tests/maxsize_worker.py."""
+    out = tmp_path / "maxsize.json"
+    n = min(torch.cuda.device_count(), 8)
+    subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n),
+                    "--master-addr", "127.0.0.1", "--master-port", "29733", os.path.join(common.ROOT, "tests", "maxsize_worker.py"),
+                    "65536", str(out)], check=True, timeout=900)
+    res = json.load(open(out))
+    assert res["cells"] == 2 ** 32 and res["world"] == n
+    for r in res["ranks"]:
+        assert r["bad"] == [], "rank %d: bands differ from the 64-bit oracle: %r" % (r["rank"], r["bad"])
+        assert r["rows_checked"] >= 96
+    assert sum(r["rows_checked"] for r in res["ranks"]) == 2 * (192) - 2 * 12 + (n - 1) * (192 - 24)
+
+
 @pytest.mark.parametrize("p2p", [False, True])
 def test_sharded_solve_with_static_tile_skipping_equals_one_field(libepic_built, p2p):
     """Solve to epsilon on three slabs with static-tile skipping on (edge tiles always run): iteration count,
