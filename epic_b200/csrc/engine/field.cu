@@ -1594,8 +1594,14 @@ int Field::paths_view(const FieldView2D &view, uint32_t count, const float *star
     }
     bool running = true;
     for (uint32_t launch = 0; running && result == kSuccess; ++launch) {
-        path_2d_kernel<<<(count + kPathWarps - 1) / kPathWarps, 32 * kPathWarps, 0, stream_>>>(
-            view, count, d_starts, step, cd, max_floats, chunk, d_states, d_out, d_emitted, launch == 0 ? 1u : 0u);
+        // a whole-grid field (one slab that starts at row 0) gets the kernel without the slab lookup
+        if (view.nslabs == 1 && view.grow0[0] == 0) {
+            path_2d_kernel<false><<<(count + kPathWarps - 1) / kPathWarps, 32 * kPathWarps, 0, stream_>>>(
+                view, count, d_starts, step, cd, max_floats, chunk, d_states, d_out, d_emitted, launch == 0 ? 1u : 0u);
+        } else {
+            path_2d_kernel<true><<<(count + kPathWarps - 1) / kPathWarps, 32 * kPathWarps, 0, stream_>>>(
+                view, count, d_starts, step, cd, max_floats, chunk, d_states, d_out, d_emitted, launch == 0 ? 1u : 0u);
+        }
         launches_++;
         if (cudaGetLastError() != cudaSuccess) {
             result = kKernelExecution;

@@ -337,28 +337,32 @@ __device__ __forceinline__ uint32_t f2u_x86(float f)
     return (uint32_t)(uint64_t)__float2ll_rz(f);
 }
 
-__device__ __forceinline__ uint32_t slab_of(const FieldView2D &f, uint32_t yc)
+// Row yc (inside the grid) of the field: where its potentials and its free bits start.  MULTI = false is the
+// whole-grid field (one slab, everything about it a kernel-parameter constant); MULTI = true finds the slab that
+// owns the row first.  A streamline is a chain of dependent instructions issued by one warp, so every instruction
+// of the address arithmetic is latency on the critical path: the taps of a bilinear lookup share their two rows.
+struct RowRef {
+    const float *u;
+    const uint32_t *mask;
+};
+
+template <bool MULTI>
+__device__ __forceinline__ RowRef row_ref(const FieldView2D &f, uint32_t yc)
 {
-    uint32_t i = 0;
-    while (i + 1u < f.nslabs && yc >= f.row_end[i]) {
-        ++i;
+    RowRef r;
+    if (MULTI) {
+        uint32_t i = 0;
+        while (i + 1u < f.nslabs && yc >= f.row_end[i]) {
+            ++i;
+        }
+        const uint64_t b = (uint64_t)((int64_t)yc - f.grow0[i]);
+        r.u = f.u[i] + b * f.pitch;
+        r.mask = f.mask[i] + b * f.mask_wpr;
+    } else {
+        r.u = f.u[0] + (uint64_t)yc * f.pitch;            // a whole-grid field starts at global row 0
+        r.mask = f.mask[0] + (uint64_t)yc * f.mask_wpr;
     }
-    return i;
-}
-
-// Loads for cell (xc, yc), which must lie inside the grid.
-__device__ __forceinline__ uint32_t cell_mask_word(const FieldView2D &f, uint32_t xc, uint32_t yc)
-{
-    const uint32_t s = slab_of(f, yc);
-    const uint64_t b = (uint64_t)((int64_t)yc - f.grow0[s]);
-    return __ldg(f.mask[s] + b * f.mask_wpr + (xc >> 5));
-}
-
-__device__ __forceinline__ float cell_u(const FieldView2D &f, uint32_t xc, uint32_t yc)
-{
-    const uint32_t s = slab_of(f, yc);
-    const uint64_t b = (uint64_t)((int64_t)yc - f.grow0[s]);
-    return __ldg(f.u[s] + b * f.pitch + xc);
+    return r;
 }
 
 // Everything one bilinear potential lookup (harmonic_path_cpu.cpp:41-82) reads, fetched with INDEPENDENT loads
@@ -373,6 +377,7 @@ struct PotentialTaps {
     float x, y;
 };
 
+template <bool MULTI>
 __device__ __forceinline__ void potential_fetch(const FieldView2D &f, float x, float y, PotentialTaps &t)
 {
     t.x = x;
@@ -387,14 +392,16 @@ __device__ __forceinline__ void potential_fetch(const FieldView2D &f, float x, f
     t.centre_u = 0.0f;
     t.tl = t.tr = t.bl = t.br = 0.0f;
     if (t.centre_in) {
-        t.centre_word = cell_mask_word(f, t.xr, t.yb);
-        t.centre_u = cell_u(f, t.xr, t.yb);
-    }
-    if (t.taps_in) {
-        t.tl = cell_u(f, t.xl, t.yt);
-        t.tr = cell_u(f, t.xr, t.yt);
-        t.bl = cell_u(f, t.xl, t.yb);
-        t.br = t.centre_u;
+        const RowRef rb = row_ref<MULTI>(f, t.yb);
+        t.centre_word = __ldg(rb.mask + (t.xr >> 5));
+        t.centre_u = __ldg(rb.u + t.xr);
+        if (t.taps_in) {
+            const RowRef rt = row_ref<MULTI>(f, t.yt);
+            t.tl = __ldg(rt.u + t.xl);
+            t.tr = __ldg(rt.u + t.xr);
+            t.bl = __ldg(rb.u + t.xl);
+            t.br = t.centre_u;
+        }
     }
 }
 
@@ -421,10 +428,11 @@ __device__ __forceinline__ int potential_eval(const PotentialTaps &t, float *out
     return kPathOk;
 }
 
+template <bool MULTI>
 __device__ int potential_2d(const FieldView2D &f, float x, float y, float *out)
 {
     PotentialTaps t;
-    potential_fetch(f, x, y, t);
+    potential_fetch<MULTI>(f, x, y, t);
     return potential_eval(t, out);
 }
 
@@ -444,13 +452,14 @@ __device__ __forceinline__ int gradient_from(int r, float v0, float v1, float v2
     return kPathOk;
 }
 
+template <bool MULTI>
 __device__ int gradient_2d(const FieldView2D &f, float x, float y, float cd, float *px, float *py)
 {
     PotentialTaps t0, t1, t2, t3;
-    potential_fetch(f, __fsub_rn(x, cd), y, t0);
-    potential_fetch(f, __fadd_rn(x, cd), y, t1);
-    potential_fetch(f, x, __fsub_rn(y, cd), t2);
-    potential_fetch(f, x, __fadd_rn(y, cd), t3);
+    potential_fetch<MULTI>(f, __fsub_rn(x, cd), y, t0);
+    potential_fetch<MULTI>(f, __fadd_rn(x, cd), y, t1);
+    potential_fetch<MULTI>(f, x, __fsub_rn(y, cd), t2);
+    potential_fetch<MULTI>(f, x, __fadd_rn(y, cd), t3);
     float v0 = 0.0f, v1 = 0.0f, v2 = 0.0f, v3 = 0.0f;
     int r = potential_eval(t0, &v0);
     r += potential_eval(t1, &v1);
@@ -478,6 +487,7 @@ struct PathState {        // lets a long path continue across launches
 // relaunches while any path is still running.  `points` counts over all launches.
 constexpr int kPathWarps = 4;
 
+template <bool MULTI>
 __global__ void __launch_bounds__(32 * kPathWarps)
 path_2d_kernel(FieldView2D f, uint32_t count, const float *__restrict__ starts, float step, float cd,
                uint64_t max_floats, uint32_t chunk, PathState *states, float *__restrict__ out,
@@ -488,76 +498,79 @@ path_2d_kernel(FieldView2D f, uint32_t count, const float *__restrict__ starts, 
     if (i >= count) {
         return;     // warp-uniform
     }
-    PathState s;
+    // The state every lane carries: the current point, counters, status.  The five previous points (the stuck
+    // test's history, most recent first) are spread over the warp instead: lane h < 5 keeps entry h, so that
+    // "shift the history" is two shuffles and "distance to entry h" needs no selection.
+    float x, y, hx = 0.0f, hy = 0.0f;
+    uint32_t nhist, points;
+    int status;
     float *o = out + (uint64_t)i * chunk * 2;
     uint32_t n = 0;
     if (first_launch) {
-        s.x = starts[2 * i];
-        s.y = starts[2 * i + 1];
-        for (int h = 0; h < 5; ++h) {
-            s.hx[h] = s.hy[h] = 0.0f;
-        }
-        s.nhist = 0;
-        s.points = 0;
-        s.status = -1;
-        const uint32_t xc = f2u_x86(__fadd_rn(s.x, 0.5f)), yc = f2u_x86(__fadd_rn(s.y, 0.5f));
+        x = starts[2 * i];
+        y = starts[2 * i + 1];
+        nhist = 0;
+        points = 0;
+        status = -1;
+        const uint32_t xc = f2u_x86(__fadd_rn(x, 0.5f)), yc = f2u_x86(__fadd_rn(y, 0.5f));
         bool blocked = xc >= f.m1 || yc >= f.m0;
         if (!blocked) {
-            const bool locked = ((cell_mask_word(f, xc, yc) >> (xc & 31u)) & 1u) == 0u;
-            blocked = locked && cell_u(f, xc, yc) < 0.0f;
+            const RowRef rr = row_ref<MULTI>(f, yc);
+            const bool locked = ((__ldg(rr.mask + (xc >> 5)) >> (xc & 31u)) & 1u) == 0u;
+            blocked = locked && __ldg(rr.u + xc) < 0.0f;
         }
         if (blocked) {
-            s.status = kPathInvalidLocation;
+            status = kPathInvalidLocation;
         } else {
             if (lane == 0) {
-                o[0] = s.x;
-                o[1] = s.y;
+                o[0] = x;
+                o[1] = y;
             }
             n = 1;
-            s.points = 1;
+            points = 1;
         }
     } else {
-        s = states[i];
+        const PathState &s = states[i];
+        x = s.x;
+        y = s.y;
+        nhist = s.nhist;
+        points = s.points;
+        status = s.status;
+        if (lane < 5u) {
+            hx = s.hx[lane];
+            hy = s.hy[lane];
+        }
     }
     const float half_step = __fdiv_rn(step, 2.0f);
     const uint32_t which = lane & 3u;      // this lane's potential of the central difference
-    while (s.status == -1 && n < chunk) {
+    while (status == -1 && n < chunk) {
         // ---- this lane's share of the step -------------------------------------------------------------
         // EVERY lane runs the same instructions (no lane-dependent branch, which would serialise the pieces):
         // the potential at (x -/+ cd, y) or (x, y -/+ cd) chosen by lane & 3, the lock bit of the current cell,
-        // and the distance to one of the previous points.  The three chains are independent of each other, so
+        // and the distance to this lane's history entry.  The three chains are independent of each other, so
         // their latencies overlap inside the one instruction stream.
-        const float qx = (which == 0u) ? __fsub_rn(s.x, cd) : ((which == 1u) ? __fadd_rn(s.x, cd) : s.x);
-        const float qy = (which == 2u) ? __fsub_rn(s.y, cd) : ((which == 3u) ? __fadd_rn(s.y, cd) : s.y);
+        const float qx = (which == 0u) ? __fsub_rn(x, cd) : ((which == 1u) ? __fadd_rn(x, cd) : x);
+        const float qy = (which == 2u) ? __fsub_rn(y, cd) : ((which == 3u) ? __fadd_rn(y, cd) : y);
         PotentialTaps t;
-        potential_fetch(f, qx, qy, t);
+        potential_fetch<MULTI>(f, qx, qy, t);
         // loop condition of harmonic_path_cpu.cpp:185-187, evaluated on the current point
-        const uint32_t xc = f2u_x86(__fadd_rn(s.x, 0.5f)), yc = f2u_x86(__fadd_rn(s.y, 0.5f));
+        const uint32_t xc = f2u_x86(__fadd_rn(x, 0.5f)), yc = f2u_x86(__fadd_rn(y, 0.5f));
         const bool outside = xc >= f.m1 || yc >= f.m0;
-        const uint32_t cword = outside ? 0u : cell_mask_word(f, xc, yc);
+        const uint32_t cword = outside ? 0u : __ldg(row_ref<MULTI>(f, yc).mask + (xc >> 5));
         const bool stop_here = outside || ((cword >> (xc & 31u)) & 1u) == 0u;
-        // distance to the (lane mod 8)-th previous point (lanes whose index is not a valid history entry are ignored)
-        const uint32_t hidx = lane & 7u;
-        float hxl = s.hx[0], hyl = s.hy[0];
-#pragma unroll
-        for (int h = 1; h < 5; ++h) {
-            if (hidx == (uint32_t)h) {
-                hxl = s.hx[h];
-                hyl = s.hy[h];
-            }
-        }
-        const double ddx = (double)__fsub_rn(s.x, hxl), ddy = (double)__fsub_rn(s.y, hyl);
+        // the stuck test (harmonic_path_cpu.cpp:121-151): lane h measures the distance to the h-th previous point
+        const double ddx = (double)__fsub_rn(x, hx), ddy = (double)__fsub_rn(y, hy);
         const float dist = __double2float_rn(__dsqrt_rn(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy))));
-        const bool near = hidx < s.nhist && dist < half_step;
+        const bool near = lane < nhist && dist < half_step;
         float v = 0.0f;
         const int pr = potential_eval(t, &v);
         // ---- together ------------------------------------------------------------------------------------
         bool stop = __any_sync(0xffffffffu, stop_here || near);
-        if (!stop && (uint64_t)s.points * 2ull >= max_floats) {
+        if (!stop && (uint64_t)points * 2ull >= max_floats) {
             stop = true;
         }
         if (stop) {
-            s.status = (s.points <= 2u) ? kPathInvalidPath : kPathOk;
+            status = (points <= 2u) ? kPathInvalidPath : kPathOk;
             break;
         }
         const int bad = __any_sync(0xffffffffu, pr != kPathOk) ? 1 : 0;
@@ -565,30 +578,35 @@ path_2d_kernel(FieldView2D f, uint32_t count, const float *__restrict__ starts, 
         const float v2 = __shfl_sync(0xffffffffu, v, 2), v3 = __shfl_sync(0xffffffffu, v, 3);
         float gx, gy;
         if (gradient_from(bad, v0, v1, v2, v3, cd, &gx, &gy) != kPathOk) {
-            s.status = kPathInvalidGradient;
+            status = kPathInvalidGradient;
             break;
         }
-#pragma unroll
-        for (int h = 4; h > 0; --h) {
-            s.hx[h] = s.hx[h - 1];
-            s.hy[h] = s.hy[h - 1];
+        // history: entry h <- entry h - 1, entry 0 <- the current point
+        const float px = __shfl_up_sync(0xffffffffu, hx, 1), py = __shfl_up_sync(0xffffffffu, hy, 1);
+        hx = (lane == 0u) ? x : px;
+        hy = (lane == 0u) ? y : py;
+        if (nhist < 5u) {
+            nhist++;
         }
-        s.hx[0] = s.x;
-        s.hy[0] = s.y;
-        if (s.nhist < 5u) {
-            s.nhist++;
-        }
-        s.x = __fadd_rn(s.x, __fmul_rn(gx, step));
-        s.y = __fadd_rn(s.y, __fmul_rn(gy, step));
+        x = __fadd_rn(x, __fmul_rn(gx, step));
+        y = __fadd_rn(y, __fmul_rn(gy, step));
         if (lane == 0) {
-            o[2 * n] = s.x;
-            o[2 * n + 1] = s.y;
+            o[2 * n] = x;
+            o[2 * n + 1] = y;
         }
         n++;
-        s.points++;
+        points++;
+    }
+    if (lane < 5u) {
+        states[i].hx[lane] = hx;
+        states[i].hy[lane] = hy;
     }
     if (lane == 0) {
-        states[i] = s;
+        states[i].x = x;
+        states[i].y = y;
+        states[i].nhist = nhist;
+        states[i].points = points;
+        states[i].status = status;
         emitted[i] = n;
     }
 }
@@ -597,9 +615,9 @@ __global__ void potential_gradient_kernel(FieldView2D f, float x, float y, float
                                           float *out, int *ret)
 {
     if (want_gradient) {
-        *ret = gradient_2d(f, x, y, cd, out, out + 1);
+        *ret = gradient_2d<true>(f, x, y, cd, out, out + 1);
     } else {
-        *ret = potential_2d(f, x, y, out);
+        *ret = potential_2d<true>(f, x, y, out);
     }
 }
 

@@ -114,6 +114,10 @@ REFERENCE_EXPORTS = {
 
 _F = ct.c_void_p
 EXTENSION_EXPORTS = {
+    "harmonic_legacy_sor_2d_float_gpu": (ct.c_uint, ct.c_uint, ct.c_float, ct.c_float, _P(ct.c_uint),
+                                         _P(ct.c_float), _P(ct.c_uint)),
+    "harmonic_legacy_sor_2d_double_gpu": (ct.c_uint, ct.c_uint, ct.c_double, ct.c_double, _P(ct.c_uint),
+                                          _P(ct.c_double), _P(ct.c_uint)),
     "harmonic_compute_potential_2d_gpu": (_H, ct.c_float, ct.c_float, _P(ct.c_float)),
     "harmonic_compute_gradient_2d_gpu": (_H, ct.c_float, ct.c_float, ct.c_float, _P(ct.c_float), _P(ct.c_float)),
     "harmonic_compute_path_2d_gpu": (_H, ct.c_float, ct.c_float, ct.c_float, ct.c_float, ct.c_uint,

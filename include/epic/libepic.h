@@ -133,6 +133,15 @@ EPIC_API int harmonic_legacy_compute_path_2d_cpu(unsigned int w, unsigned int h,
                                                  EPIC_REF(double *) path);
 EPIC_API int harmonic_legacy_free_path_cpu(EPIC_REF(double *) path);
 
+/* ---- Extension: the legacy linear-space SOR on the GPU (the reference has it on the host only,
+ * harmonic_legacy_cpu.cpp:36-141).  Same arguments and results as the *_cpu twins above, bit for bit: the lexicographic
+ * in-place sweep is executed as waves of independent cells (epic_b200/csrc/abi/legacy_gpu.cu).  long double is x87
+ * arithmetic and stays host-only. ---- */
+EPIC_API int harmonic_legacy_sor_2d_float_gpu(unsigned int w, unsigned int h, float epsilon, float omega,
+                                              unsigned int *locked, float *u, EPIC_REF(unsigned int) iter);
+EPIC_API int harmonic_legacy_sor_2d_double_gpu(unsigned int w, unsigned int h, double epsilon, double omega,
+                                               unsigned int *locked, double *u, EPIC_REF(unsigned int) iter);
+
 /* ---- Extensions of this library (not in the reference): streamlines on the DEVICE-resident field,
  * so that a path or a cell query does not need harmonic_get_potential_values_gpu's full-field copy
  * (the reference's anytime node does one per service call, src/epic_navigation_node_harmonic.cpp:531,622).

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol(libepic_built):
     out = subprocess.run(["nm", "-D", "--defined-only", le.LIB_PATH], capture_output=True, text=True, check=True).stdout
     exported = {line.split()[-1] for line in out.splitlines() if " T " in line}
     declared = declared_symbols()
-    assert len(declared) == 30 + 4 + 3 + 4 + 23 + 1   # reference, device streamlines, pose lists, dense map ingest, slab API, stats
+    assert len(declared) == 30 + 4 + 3 + 4 + 23 + 1 + 2   # reference, device streamlines, pose lists, dense map ingest, slab API, stats, legacy SOR on the GPU
     assert declared <= exported, "missing exports: %s" % sorted(declared - exported)
     assert set(le.ALL_EXPORTS) == declared, "Python binding table and headers disagree"
     assert len(le.REFERENCE_EXPORTS) == 30
