@@ -98,6 +98,22 @@ int Grid::create(Grid **out, unsigned n, const uint64_t *gm, const FieldConfig &
     const uint64_t min_rows = (n == 2) ? (uint64_t)std::max(4 * T, 16) : 8;
     size_t want = cfg.ndevices > 1 ? (size_t)cfg.ndevices : 1;
     want = (size_t)std::max<uint64_t>(1, std::min<uint64_t>(want, gm[0] / min_rows));
+    {
+        // A small map is bound by launch latency, not by arithmetic: sharding it only adds exchanges.  Use a device
+        // per EPIC_MIN_SLAB_CELLS cells (default 2^20; the demo maps stay on one GPU, a 4096^2 grid uses all
+        // eight).  0 takes the device list literally (tests).
+        uint64_t min_cells = 1ull << 20;
+        if (const char *e = getenv("EPIC_MIN_SLAB_CELLS")) {
+            min_cells = strtoull(e, nullptr, 10);
+        }
+        uint64_t cells = 1;
+        for (unsigned i = 0; i < n; ++i) {
+            cells *= gm[i];
+        }
+        if (min_cells > 0) {
+            want = (size_t)std::max<uint64_t>(1, std::min<uint64_t>(want, cells / min_cells));
+        }
+    }
     if (want <= 1) {
         if (cfg.ndevices >= 1) {
             cfg.device = cfg.devices[0];

@@ -36,6 +36,7 @@ def device_lists():
 @pytest.mark.parametrize("case", ["box64", "basic", "proc_maze", "random256", "random48x3"])
 def test_complete_gpu_sharded_behind_the_abi(golden, libepic_built, monkeypatch, devices, case):
     monkeypatch.setenv("EPIC_DEVICES", devices)
+    monkeypatch.setenv("EPIC_MIN_SLAB_CELLS", "0")     # take the list literally, however small the grid
     u, locked, eps, stagger = common.case_input(case)
     h = Harmonic(u.copy(), locked.copy(), eps, stagger)
     assert libepic_built.harmonic_complete_gpu(ct.byref(h), 1024) == 0
@@ -50,6 +51,7 @@ def test_checkpoints_and_paths_sharded_behind_the_abi(golden, libepic_built, mon
     """update / update_and_check call by call (host-side max of the slabs' deltas), then streamlines on the
     device-resident sharded field: the kernels read the slabs through a multi-slab view."""
     monkeypatch.setenv("EPIC_DEVICES", devices)
+    monkeypatch.setenv("EPIC_MIN_SLAB_CELLS", "0")     # take the list literally, however small the grid
     make = lambda u, l, e, s: common.LibepicSolver(u, l, e, s, "gpu")   # noqa: E731
     common.check_checkpoints(make, "proc_maze", golden["proc_maze"])
     u, locked, eps, stagger = common.case_input("box64")
@@ -72,6 +74,7 @@ def test_checkpoints_and_paths_sharded_behind_the_abi(golden, libepic_built, mon
 def test_set_cells_and_update_model_sharded(libepic_built, monkeypatch, devices):
     """Sparse edits (also into ghost layers: rows next to a slab boundary) and a full re-upload."""
     monkeypatch.setenv("EPIC_DEVICES", devices)
+    monkeypatch.setenv("EPIC_MIN_SLAB_CELLS", "0")     # take the list literally, however small the grid
     shape = (160, 130)
     u, locked = grids.random_obstacles(shape, 0.15, 3, seed=5)
     s = common.LibepicSolver(u.copy(), locked.copy(), 1e-3, 50, "gpu")
@@ -99,6 +102,7 @@ def test_replayed_callers_with_epic_devices(libepic_built, monkeypatch, tmp_path
     """The ROS-free replay of the plugin / the node, unchanged, with the library sharding behind the ABI."""
     import json
     monkeypatch.setenv("EPIC_DEVICES", devices)
+    monkeypatch.setenv("EPIC_MIN_SLAB_CELLS", "0")     # take the list literally, however small the grid
     exe = replay.build(str(tmp_path / "replay_ours"))
     with open(replay.GOLDEN) as f:
         gold = json.load(f)[scenario]
@@ -112,6 +116,7 @@ def test_solve_after_solve_and_updates_after_solve(libepic_built, monkeypatch):
     """Passes queued past the converged check retire as no-ops but still publish their index to the neighbours:
     the next calls on the same resident grid must neither hang nor differ."""
     monkeypatch.setenv("EPIC_DEVICES", "0,0")
+    monkeypatch.setenv("EPIC_MIN_SLAB_CELLS", "0")
     u, locked, eps, stagger = common.case_input("random_ragged")
     h = Harmonic(u.copy(), locked.copy(), eps, stagger)
     h.initialize_gpu()

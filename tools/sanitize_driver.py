@@ -17,6 +17,7 @@ from epic_b200 import grids  # noqa: E402
 from epic_b200.harmonic import Harmonic  # noqa: E402
 from oracle import oracle as orc  # noqa: E402
 
+os.environ["EPIC_MIN_SLAB_CELLS"] = "0"     # EPIC_DEVICES lists are taken literally, however small the grid
 which = sys.argv[1:] or ["plain", "solve", "sharded", "sharded3d", "d3", "paths", "edits"]
 
 
