@@ -196,9 +196,10 @@ class ShardedSolver:
                 self.run(left, False)
                 left = 0
 
-    def solve(self, epsilon, stagger, m_max=None):
+    def solve(self, epsilon, stagger, m_max=None, max_iterations=None):
         """harmonic_execute_gpu's loop: stop right after a check sweep with delta < epsilon once
-        iteration >= max(m).  Returns (iterations, delta)."""
+        iteration >= max(m).  Returns (iterations, delta).  `max_iterations` (not in the reference, whose loop
+        is unbounded) raises TimeoutError once that many iterations have run without convergence."""
         if not epsilon > 0.0 or stagger <= 0:
             raise ValueError("epsilon must be positive and stagger non-zero")
         m_max = max(self.slab.shape) if m_max is None else m_max
@@ -211,6 +212,8 @@ class ShardedSolver:
                 self.run(to_check + 1, True)
                 if self.delta < epsilon and self.iteration >= m_max:
                     return self.iteration, self.delta
+                if max_iterations is not None and self.iteration >= max_iterations:
+                    raise TimeoutError("no convergence after %d iterations (delta %g)" % (self.iteration, self.delta))
         finally:
             if hasattr(self.slab, "set_tracking"):
                 self.slab.set_tracking(False)
