@@ -335,8 +335,14 @@ int Field::create(Field **out, unsigned n, const uint64_t *gm, uint64_t row0, ui
                 f->NT_ = c.nt;
             }
         }
-        if (cfg.tile_rows > 2 * f->T_ + 1 && cfg.tile_rows <= 200) {
+        // An override must leave an output region at least as tall as the halo (TH - 2T >= T): static-tile skipping
+        // looks at the 3 x 3 neighbourhood of a tile and the peer-to-peer edge classification at the first / last
+        // tile rows, both of which assume that a tile's input does not reach beyond its direct neighbours.
+        if (cfg.tile_rows >= 3 * f->T_ && cfg.tile_rows > 2 * f->T_ + 1 && cfg.tile_rows <= 200) {
             f->TH_ = cfg.tile_rows;
+        } else if (cfg.tile_rows != 0) {
+            fprintf(stderr, "Warning[epic_b200]: EPIC_TILE_ROWS=%d does not fit %d sweeps per pass (need %d..200); ignored.\n",
+                    cfg.tile_rows, f->T_, 3 * f->T_);
         }
         if (cfg.threads == 256 || cfg.threads == 512) {
             f->NT_ = cfg.threads;

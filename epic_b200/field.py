@@ -67,6 +67,8 @@ class Field:
     def upload_u(self, u, first=None, layers=None):
         first, layers = self._layers(first, layers)
         u = np.ascontiguousarray(u, dtype=np.float32)
+        if u.shape != (layers,) + self.shape[1:]:     # the C side would read past a short buffer
+            raise ValueError("upload_u: array of shape %r does not cover %d layers of %r" % (u.shape, layers, self.shape[1:]))
         self._check("upload_u", self._lib.epic_b200_field_upload_u(
             self._h, u.ctypes.data_as(ct.POINTER(ct.c_float)), first, layers))
 
@@ -74,6 +76,8 @@ class Field:
         first, layers = self._layers(first, layers)
         if out is None:
             out = np.empty((layers,) + self.shape[1:], np.float32)
+        elif out.dtype != np.float32 or not out.flags["C_CONTIGUOUS"] or out.size != layers * int(np.prod(self.shape[1:])):
+            raise ValueError("download_u: `out` must be a C-contiguous float32 array of %d x %r values" % (layers, self.shape[1:]))
         self._check("download_u", self._lib.epic_b200_field_download_u(
             self._h, out.ctypes.data_as(ct.POINTER(ct.c_float)), first, layers))
         return out
