@@ -290,8 +290,8 @@ def reference_gpu_baseline(args):
             return {"error": "timed out after %d s" % timeout}
     # The stock build: its sweep kernels call __syncthreads() in divergent code (reference harmonic_gpu.cu:46-49,
     # :86-89), which deadlocks on Volta and later (SASS: WARPSYNC.ALL on both sides of the divergent branch;
-    # profiles/r02_reference_gpu.md).  One short attempt records that on this box; the numbers come from the build
-    # with the barriers compiled out (oracle/Makefile refgpu_nobar), through harmonic_update_gpu, which needs none.
+    # profiles/r02_reference_gpu.md).  The numbers come from the build with the barriers compiled out
+    # (oracle/Makefile refgpu_nobar), through harmonic_update_gpu, which needs none.
     if args.try_stock_reference_gpu:
         out["stock_complete_gpu_maze"] = sub(["complete", "--map", "maze"], 25)
     else:
